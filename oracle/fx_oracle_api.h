@@ -1,0 +1,74 @@
+/*
+ * fx_oracle_api.h -- C API shared by the two CPU checkers under oracle/.
+ * TEST INFRASTRUCTURE ONLY: nothing under feature-extractor_b200/ may include, link or load this.
+ *
+ *   oracle/_ref/libfxref.so   the reference's own headers (the .h files under /root/reference/Source), compiled
+ *                             headless against oracle/juce_shim/JuceHeader.h (ref_driver.cpp)
+ *   oracle/libfxoracle.so     plain-C restatement of the same path (fx_oracle.c)
+ *
+ * Both export the same entry points so the tests can swap one for the other.
+ */
+#ifndef FX_ORACLE_API_H
+#define FX_ORACLE_API_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* feature slots follow AudioFeatures::eAudioFeature (RealTimeAnalyser.h:17-32) */
+enum {
+    FXO_ONSET = 0, FXO_RMS, FXO_F0, FXO_CENTROID, FXO_SPREAD, FXO_FLATNESS, FXO_LER, FXO_FLUX,
+    FXO_SLOPE, FXO_HER, FXO_OER, FXO_INHARM, FXO_NUM_FEATURES
+};
+
+/* per-frame diagnostics (float[FXO_NUM_DIAG]) */
+enum {
+    FXO_DIAG_TRUE_OER = 0,     /* log-mapped odd/even ratio the reference computes but never stores (RealTimeAnalyser.h:171) */
+    FXO_DIAG_LAG,              /* integer pitch lag (PitchAnalyser.h:161-190) */
+    FXO_DIAG_PITCH_MARGIN,     /* smallest relative margin of any comparison that decided the lag  (port only, else -1) */
+    FXO_DIAG_NUM_PEAKS,        /* number of peak bins (HarmonicCharacteristics.h:115-145)          (port only, else -1) */
+    FXO_DIAG_PEAK_MARGIN,      /* smallest relative margin of any peak / bin-index decision        (port only, else -1) */
+    FXO_DIAG_FLAT_COUNT,       /* bins gated into the flatness product (SpectralCharacteristics.h:89-94) (port only, else -1) */
+    FXO_DIAG_FLAT_MARGIN,      /* smallest relative distance of a bin magnitude to the gate eps    (port only, else -1) */
+    FXO_DIAG_GATE_MARGIN,      /* smallest relative margin of the silence gates (0.05, 0.005, 1e-4) (port only, else -1) */
+    FXO_DIAG_ONSET_MARGIN,     /* smallest relative margin of the onset detector's comparisons     (port only, else -1) */
+    FXO_DIAG_FLAT_STATE,       /* flatness product: 0 finite, 1 underflowed to 0, 2 overflowed to inf, 3 frame gated silent (port only, else -1) */
+    FXO_NUM_DIAG
+};
+
+typedef struct fxo_config {
+    int    window;            /* N, power of two                                  */
+    int    hop;               /* H; mode 0 requires H == N/2                      */
+    double sample_rate;
+    float  gain;              /* AudioDataCollector::setGain                       */
+    int    onset_type;        /* OnsetDetector::eOnsetDetectionType: 0 spectral, 1 amplitude (default), 2 combination */
+    int    onset_hist;        /* 5                                                */
+    float  onset_multiplier;  /* 1.7                                              */
+    int    rms_pushes;        /* 2 = both analyser bodies push RMS (reference wiring), 1 = spectral only */
+    int    mode;              /* 0 = A: verbatim collector/overlapper/run() bodies; 1 = B: re-sequenced per-frame calls, any hop */
+} fxo_config;
+
+void fxo_default_config (fxo_config* cfg);
+
+/* which checker is this: "reference" or "port" */
+const char* fxo_kind (void);
+
+/* Analyse one track.  Outputs are [frames][12] raw (values as pushed into AudioFeatures), [frames][12]
+ * smoothed (AudioFeatures::getValue after both analyser bodies of the hop), [frames][FXO_NUM_DIAG].
+ * Any output pointer may be NULL.  Returns the number of frames written (min (n_samples / hop, max_frames)). */
+long fxo_analyse_track (const fxo_config* cfg, const float* audio, long n_samples,
+                        float* raw, float* smooth, float* diag, long max_frames);
+
+/* Same over n_tracks rows of `audio` (row stride in samples), contiguous track ranges per thread. */
+long fxo_analyse_tracks (const fxo_config* cfg, const float* audio, long n_tracks, long track_stride, long n_samples,
+                         float* raw, float* smooth, float* diag, long max_frames, int n_threads);
+
+/* The FFT the reference reaches through RealTimeFFT (RealTimeAudioAnalysis.h:167-177):
+ * forward: N reals -> 2N interleaved floats; inverse: 2N interleaved -> d[0..N) = Re/N, d[N..2N) = Im/N. */
+void fxo_fft_forward (const float* frame, int n, float* out_2n);
+void fxo_fft_inverse (float* inout_2n, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
