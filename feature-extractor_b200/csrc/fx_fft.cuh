@@ -1,0 +1,198 @@
+// fx_fft.cuh -- shared-memory N-point complex FFT for one CTA (sm_100a), N = R1 * 16 * 16,
+// R1 in {4, 8, 16}  ->  N in {1024, 2048, 4096}, T = N / 16 threads, 16 complex points per thread.
+//
+// Replaces juce::FFT as reached through RealTimeFFT (Source/RealTimeAudioAnalysis.h:159-189).
+//
+// Decimation in frequency, three register-resident stages (radix R1, 16, 16) with two exchanges
+// through shared memory:
+//   n = n1 * 256 + m            (m = n2 * 16 + n3)        k = k1 + R1 * k2 + 16 * R1 * k3
+//   stage 1: butterfly m   : R1-point DFT over n1, twiddle W_N^(m k1)     -> ex[k1][m]
+//   stage 2: (k1, n3)      : 16-point DFT over n2, twiddle W_256^(n3 k2)  -> ex[k1][k2][n3]   (in place)
+//   stage 3: (k1, k2)      : 16-point DFT over n3                         -> X[k]  in registers
+// The exchange buffer is addressed with a 17/16 skew (phys (a) = a + (a >> 4)) so that the row accesses
+// of stage 2, the column accesses of stage 3 and the stride-R1 natural-order store are all conflict free.
+// Twiddles come from tables evaluated in double on the host and rounded to fp32 (as JUCE does).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fx {
+
+__device__ __forceinline__ int phys (int a) { return a + (a >> 4); }
+
+__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+
+// a * w (forward) or a * conj (w) (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 cmulw (float2 a, float2 w)
+{
+    if (INV) return make_float2 (a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+    else     return make_float2 (a.x * w.x - a.y * w.y, a.y * w.x + a.x * w.y);
+}
+
+// multiply by -i (forward) / +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi (float2 a)
+{
+    if (INV) return make_float2 (-a.y, a.x);
+    else     return make_float2 (a.y, -a.x);
+}
+
+template <bool INV>
+__device__ __forceinline__ void radix2 (float2& a0, float2& a1)
+{
+    const float2 t = a0;
+    a0 = cadd (t, a1);
+    a1 = csub (t, a1);
+}
+
+// 4-point DFT in place: slot j <- X[j]
+template <bool INV>
+__device__ __forceinline__ void radix4 (float2& a0, float2& a1, float2& a2, float2& a3)
+{
+    const float2 t0 = cadd (a0, a2), t1 = csub (a0, a2);
+    const float2 t2 = cadd (a1, a3), t3 = mul_mi<INV> (csub (a1, a3));
+    a0 = cadd (t0, t2);
+    a2 = csub (t0, t2);
+    a1 = cadd (t1, t3);
+    a3 = csub (t1, t3);
+}
+
+#define FX_C1 0.92387953251128675613f   /* cos (pi / 8) */
+#define FX_S1 0.38268343236508977173f   /* sin (pi / 8) */
+#define FX_R2 0.70710678118654752440f   /* sqrt (1/2)  */
+
+// R-point DFT in registers; afterwards slot s holds X[out_index<R> (s)].
+template <int R> __device__ __forceinline__ constexpr int out_index (int s)
+{
+    return R == 16 ? ((s >> 2) + 4 * (s & 3)) : (R == 8 ? ((s >> 2) + 2 * (s & 3)) : s);
+}
+// inverse of out_index: the slot that holds X[k]
+template <int R> __device__ __forceinline__ constexpr int slot_of (int k)
+{
+    return R == 16 ? ((k >> 2) + 4 * (k & 3)) : (R == 8 ? ((k >> 1) + 4 * (k & 1)) : k);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void butterfly (float2* v)
+{
+    if (R == 16)
+    {
+        #pragma unroll
+        for (int n0 = 0; n0 < 4; ++n0) radix4<INV> (v[n0], v[n0 + 4], v[n0 + 8], v[n0 + 12]);
+        // slot n0 + 4 ka *= W16^(n0 ka)
+        v[5]  = cmulw<INV> (v[5],  make_float2 ( FX_C1, -FX_S1));   // e = 1
+        v[6]  = cmulw<INV> (v[6],  make_float2 ( FX_R2, -FX_R2));   // e = 2
+        v[7]  = cmulw<INV> (v[7],  make_float2 ( FX_S1, -FX_C1));   // e = 3
+        v[9]  = cmulw<INV> (v[9],  make_float2 ( FX_R2, -FX_R2));   // e = 2
+        v[10] = mul_mi<INV> (v[10]);                                // e = 4
+        v[11] = cmulw<INV> (v[11], make_float2 (-FX_R2, -FX_R2));   // e = 6
+        v[13] = cmulw<INV> (v[13], make_float2 ( FX_S1, -FX_C1));   // e = 3
+        v[14] = cmulw<INV> (v[14], make_float2 (-FX_R2, -FX_R2));   // e = 6
+        v[15] = cmulw<INV> (v[15], make_float2 (-FX_C1,  FX_S1));   // e = 9
+        #pragma unroll
+        for (int ka = 0; ka < 4; ++ka) radix4<INV> (v[4 * ka], v[4 * ka + 1], v[4 * ka + 2], v[4 * ka + 3]);
+    }
+    else if (R == 8)
+    {
+        #pragma unroll
+        for (int n0 = 0; n0 < 4; ++n0) radix2<INV> (v[n0], v[n0 + 4]);
+        v[5] = cmulw<INV> (v[5], make_float2 ( FX_R2, -FX_R2));
+        v[6] = mul_mi<INV> (v[6]);
+        v[7] = cmulw<INV> (v[7], make_float2 (-FX_R2, -FX_R2));
+        radix4<INV> (v[0], v[1], v[2], v[3]);
+        radix4<INV> (v[4], v[5], v[6], v[7]);
+    }
+    else
+    {
+        radix4<INV> (v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Shared-memory footprint helpers (in elements)
+template <int R1> struct FftDims
+{
+    static constexpr int N       = R1 * 256;
+    static constexpr int T       = R1 * 16;            // threads
+    static constexpr int Q1      = 16 / R1;            // stage-1 butterflies per thread
+    static constexpr int ROW     = 272;                // 256 * 17 / 16
+    static constexpr int EX_LEN  = R1 * ROW;           // float2 elements in the exchange buffer (= N * 17 / 16)
+    static constexpr int TW1_LEN = (R1 - 1) * ROW;     // float2, tw1[(k1 - 1) * ROW + phys (m)] = W_N^(m k1)
+    static constexpr int TW2_LEN = 15 * 16;            // float2, tw2[(k2 - 1) * 16 + n3]        = W_256^(n3 k2)
+};
+
+// butterfly index of stage 1 that thread t handles in its q-th slot group
+//   natural:  m = t + T q                      (inputs gathered from memory)
+//   chained:  m = klow (t) + T q, klow (t) = (t >> 4) + R1 (t & 15)
+//             (inputs are the registers left by stage 3 of a previous transform: thread t holds
+//              X[klow (t) + T k3], which is exactly input n1 of butterfly q when k3 = q + Q1 n1)
+template <int R1> __device__ __forceinline__ int klow (int t) { return (t >> 4) + R1 * (t & 15); }
+
+// Stage 1 on v (slot q * R1 + n1 = input n1 of butterfly q), then twiddle and store to ex.
+template <int R1, bool INV>
+__device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __restrict__ ex, const float2* __restrict__ tw1)
+{
+    using D = FftDims<R1>;
+    #pragma unroll
+    for (int q = 0; q < D::Q1; ++q)
+    {
+        butterfly<R1, INV> (v + q * R1);
+        const int pm = phys (m0 + D::T * q);
+        #pragma unroll
+        for (int s = 0; s < R1; ++s)
+        {
+            const int k1 = out_index<R1> (s);
+            float2 val = v[q * R1 + s];
+            if (k1 > 0) val = cmulw<INV> (val, tw1[(k1 - 1) * D::ROW + pm]);
+            ex[k1 * D::ROW + pm] = val;
+        }
+    }
+}
+
+// Stage 2 in place (one 16-point butterfly per thread).  Caller syncs before and after.
+template <int R1, bool INV>
+__device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, const float2* __restrict__ tw2)
+{
+    using D = FftDims<R1>;
+    const int k1 = t >> 4, n3 = t & 15;
+    float2* row = ex + k1 * D::ROW + n3;
+    float2 v[16];
+    #pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
+    butterfly<16, INV> (v);
+    #pragma unroll
+    for (int s = 0; s < 16; ++s)
+    {
+        const int k2 = out_index<16> (s);
+        float2 val = v[s];
+        if (k2 > 0) val = cmulw<INV> (val, tw2[(k2 - 1) * 16 + n3]);
+        row[k2 * 17] = val;
+    }
+}
+
+// Stage 3: afterwards slot s of v holds X[klow (t) + T * out_index<16> (s)].
+template <int R1, bool INV>
+__device__ __forceinline__ void fft_stage3 (int t, const float2* __restrict__ ex, float2* v)
+{
+    using D = FftDims<R1>;
+    const int k1 = t >> 4, k2 = t & 15;
+    const float2* col = ex + k1 * D::ROW + k2 * 17;
+    #pragma unroll
+    for (int n3 = 0; n3 < 16; ++n3) v[n3] = col[n3];
+    butterfly<16, INV> (v);
+}
+
+// Re-order the registers left by fft_stage3 into the stage-1 input order of a chained transform:
+// out[q * R1 + n1] = X[klow + T (q + Q1 n1)].
+template <int R1>
+__device__ __forceinline__ void chain_permute (const float2* v3, float2* v1)
+{
+    using D = FftDims<R1>;
+    #pragma unroll
+    for (int q = 0; q < D::Q1; ++q)
+        #pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1)
+            v1[q * R1 + n1] = v3[slot_of<16> (q + D::Q1 * n1)];
+}
+
+} // namespace fx

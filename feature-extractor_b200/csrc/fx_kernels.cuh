@@ -1,0 +1,83 @@
+// fx_kernels.cuh -- kernel parameter blocks and launch entry points shared by fx_analyse.cu,
+// fx_post.cu and fx_engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/fx_engine.h"
+
+namespace fx {
+
+constexpr int kHistRows   = 32;   // raw feature rows carried between calls (10-tap smoothing + <=16-deep onset window + 5)
+constexpr int kMaxOnsetHist = 16;
+
+// ---- K1: per-(track, chunk) frame walker ------------------------------------------------------------
+struct AnalyseParams
+{
+    // source: this call's samples, [n_tracks][track_stride]; hop block b (0-based in this call) at b * hop
+    const float* audio;
+    long         track_stride;
+    // carry-in / carry-out overlap tail, [n_tracks][window - hop] (the last window/hop - 1 hop blocks of the stream)
+    const float* tail_in;
+    float*       tail_out;
+    long         first_hop;        // absolute hop index (since stream start) of this call's hop block 0
+    int          n_frames;         // frames (= hop blocks) per track in this call
+    int          frames_per_chunk;
+    int          n_chunks;
+    int          hop;
+    int          log2_hop;
+    int          use_bulk;         // 1: cp.async.bulk (16-byte aligned source), 0: plain loads
+    const float* gain;             // [n_tracks]
+    double       sample_rate;
+    double       bin_var;          // slope: sum ((i/M - 0.5)^2) / M evaluated on the host in the reference's order
+    float        iir_c1, iir_c2;   // pi/2 and exp (-pi/2) in fp32 (RealTimeAudioAnalysis.h:122)
+    const float2* tw1;             // global twiddle tables (fx_fft.cuh layout)
+    const float2* tw2;
+    // outputs
+    float*       raw;              // [n_tracks][n_frames][12]
+    float*       diag;             // [n_tracks][n_frames][FX_NUM_DIAG] (may be null)
+    float*       first_spec;       // [n_tracks][n_chunks][M]  Re spectrum (windowed path) of the chunk's first non-silent frame
+    float*       last_spec;        // [n_tracks][n_chunks][M]  ... of its last non-silent frame
+    int*         first_idx;        // [n_tracks][n_chunks]     frame index of the first non-silent frame, -1 if none
+};
+
+cudaError_t launch_analyse (int window, long n_tracks, const AnalyseParams& p, cudaStream_t stream);
+cudaError_t configure_analyse (int window);             // opt in to the dynamic shared memory the kernel needs
+size_t      analyse_smem_bytes (int window);
+
+// ---- K2: flux of each chunk's first non-silent frame against the carried previous spectrum ----------
+struct FluxFixParams
+{
+    int          n_frames, n_chunks, m;   // m = window / 2
+    const float* first_spec;
+    const float* last_spec;
+    const int*   first_idx;
+    const float* prev_in;          // [n_tracks][M] carried "previousBinMagnitudes" as Re values (zeros after reset)
+    float*       prev_out;
+    float*       raw;
+};
+cudaError_t launch_flux_fix (long n_tracks, const FluxFixParams& p, cudaStream_t stream);
+
+// ---- K3: AudioFeatures smoothing + OnsetDetector, a FIR along frames --------------------------------
+struct SmoothParams
+{
+    int          n_frames;
+    long         frames_before;    // frames analysed since stream start before this call
+    int          rms_pushes;
+    float*       raw;              // onset slot is written here
+    float*       smooth;           // [n_tracks][n_frames][12] (may be null)
+    float*       diag;             // onset margin written here (may be null)
+    const float* hist_in;          // [n_tracks][kHistRows][12], newest row last
+    float*       hist_out;
+    const int*   onset_type;       // [n_tracks]
+    const int*   onset_hist;
+    const float* onset_mult;
+    const long*  onset_reset;      // [n_tracks] absolute frame index at which the onset histories were last cleared
+    float*       latest;           // [n_tracks][12 + 1] smoothed vector of the newest frame + frame count (may be null)
+};
+cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t stream);
+
+// ---- synthetic workload ------------------------------------------------------------------------------
+cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
+                          double sample_rate, uint64_t seed, cudaStream_t stream);
+
+} // namespace fx

@@ -1,0 +1,281 @@
+// fx_post.cu -- the small kernels around K1 (sm_100a):
+//   K2  k_flux_fix   flux of each chunk's first non-silent frame against the carried previous spectrum, and the
+//                    carry-out of "previousBinMagnitudes" (SpectralCharacteristics.h:75-79, :121-123, :138)
+//   K3  k_smooth     AudioFeatures / ValueHistory moving averages (RealTimeAnalyser.h:70-88,
+//                    RealTimeAudioAnalysis.h:40-96) and OnsetDetector (SpectralCharacteristics.h:243-306)
+//       k_hist       carry the last raw rows to the next call
+//       k_synth      synthetic workload generator -- measurement support only
+// All citations relative to /root/reference/Source/.
+#include "fx_kernels.cuh"
+#include <math.h>
+
+namespace fx {
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (256) k_flux_fix (const FluxFixParams p)
+{
+    const long cta = blockIdx.x;
+    const int chunk = (int) (cta % p.n_chunks);
+    const long track = cta / p.n_chunks;
+    const int t = threadIdx.x;
+    const int M = p.m;
+    const int* fidx = p.first_idx + track * p.n_chunks;
+
+    __shared__ double wsum[8];
+
+    int last_chunk = -1;                       // last chunk of this call holding a non-silent frame
+    for (int c = p.n_chunks - 1; c >= 0; --c) if (fidx[c] >= 0) { last_chunk = c; break; }
+
+    // carry-out: the newest non-silent spectrum of the track
+    if (chunk == (last_chunk >= 0 ? last_chunk : 0))
+    {
+        const float* from = last_chunk >= 0 ? p.last_spec + (track * p.n_chunks + last_chunk) * (long) M
+                                            : p.prev_in + track * (long) M;
+        float* to = p.prev_out + track * (long) M;
+        for (int i = t; i < M; i += blockDim.x) to[i] = from[i];
+    }
+
+    const int fi = fidx[chunk];
+    if (fi < 0) return;
+
+    const float* prev = p.prev_in + track * (long) M;
+    for (int c = chunk - 1; c >= 0; --c)
+        if (fidx[c] >= 0) { prev = p.last_spec + (track * p.n_chunks + c) * (long) M; break; }
+    const float* cur = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
+
+    double flux = 0.0;
+    for (int i = t; i < M; i += blockDim.x)
+    {
+        const double c = (double) cur[i], q = (double) prev[i];
+        const double diff = c * c - q * q;                            // SpectralCharacteristics.h:76
+        if (diff > 0.0) flux += diff;                                 // :77-79
+    }
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) flux += __shfl_xor_sync (0xffffffffu, flux, off);
+    if ((t & 31) == 0) wsum[t >> 5] = flux;
+    __syncthreads();
+    if (t == 0)
+    {
+        double total = 0.0;
+        for (int w = 0; w < (int) (blockDim.x >> 5); ++w) total += wsum[w];
+        const float max_flux = (float) (M * (M + 1)) / 2.0f;          // :111
+        p.raw[(track * p.n_frames + fi) * FX_NUM_FEATURES + FX_FLUX] = (float) (total / (double) max_flux);
+    }
+}
+
+cudaError_t launch_flux_fix (long n_tracks, const FluxFixParams& p, cudaStream_t stream)
+{
+    const long grid = n_tracks * p.n_chunks;
+    if (grid <= 0) return cudaSuccess;
+    k_flux_fix<<<(unsigned) grid, 256, 0, stream>>> (p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* raw_row (const SmoothParams& p, long track, long j)
+{
+    const long rel = j - p.frames_before;
+    if (rel >= 0) return p.raw + (track * p.n_frames + rel) * FX_NUM_FEATURES;
+    return p.hist_in + (track * kHistRows + (kHistRows + rel)) * FX_NUM_FEATURES;
+}
+
+// smoothed RMS as RealTimeSpectralAnalyser::detectOnset reads it (RealTimeAnalyser.h:239): after the spectral
+// body's push of frame j, before the harmonic body's
+__device__ __forceinline__ float amp_at_spectral_time (const SmoothParams& p, long track, long j)
+{
+    float total = 0.0f;
+    if (p.rms_pushes >= 2)
+    {
+        if (j - 5 >= 0) total += raw_row (p, track, j - 5)[FX_RMS];
+        for (long q = j - 4; q < j; ++q)
+            if (q >= 0) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
+        total += raw_row (p, track, j)[FX_RMS];
+        const long rec = 2 * j + 1 < 10 ? 2 * j + 1 : 10;
+        return total / (float) (int) rec;
+    }
+    for (long q = j - 9; q <= j; ++q)
+        if (q >= 0) total += raw_row (p, track, q)[FX_RMS];
+    const long rec = j + 1 < 10 ? j + 1 : 10;
+    return total / (float) (int) rec;
+}
+
+__device__ __forceinline__ float relmarginf (float a, float b)
+{
+    const float m = fmaxf (fabsf (a), fabsf (b));
+    return (m > 0.0f) ? fabsf (a - b) / m : 0.0f;
+}
+
+__global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_tracks)
+{
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tracks * p.n_frames) return;
+    const long track = idx / p.n_frames;
+    const int f = (int) (idx % p.n_frames);
+    const long g = p.frames_before + f;                       // absolute frame index since stream start
+    float* row = p.raw + (track * p.n_frames + f) * FX_NUM_FEATURES;
+
+    // ---- onset (spectral body, after the flux / RMS pushes of frame g) -----------------------------------
+    const int L = p.onset_hist[track];
+    const int type = p.onset_type[track];
+    const float mult = p.onset_mult[track];
+    float onset = 0.0f, om = 1.0f;
+    if (g - p.onset_reset[track] + 1 >= L)                    // SpectralCharacteristics.h:253-258: histories full
+    {
+        float am[kMaxOnsetHist], sf[kMaxOnsetHist];
+        float tot_am = 0.0f, tot_sf = 0.0f;
+        for (int i = 0; i < L; ++i)
+        {
+            const long j = g - L + 1 + i;
+            am[i] = amp_at_spectral_time (p, track, j);
+            sf[i] = 0.0f + raw_row (p, track, j)[FX_FLUX];    // depth-1 history: getValue = (0 + v) / 1
+            tot_am += am[i];                                  // ValueHistory::getTotal, oldest first
+            tot_sf += sf[i];
+        }
+        const float mean_sf = tot_sf / (float) L, mean_am = tot_am / (float) L;           // :260-261
+        int cand = L - 1;                                                                 // :263
+        if (type == 0 || type == 2) cand = L / 2;                                         // :265-266
+        const float cand_sf = sf[cand], cand_am = am[cand];
+        bool ok = true;
+        om = fminf (om, relmarginf (cand_am, 0.01f));
+        if (cand_am < 0.01f) ok = false;                                                  // :271-274
+        for (int i = 0; ok && i < L; ++i)
+        {
+            if (i == cand) continue;
+            if (type == 1 || type == 2) { om = fminf (om, relmarginf (am[i], cand_am)); if (am[i] >= cand_am) ok = false; }    // :283
+            if (ok && (type == 0 || type == 2)) { om = fminf (om, relmarginf (sf[i], cand_sf)); if (sf[i] >= cand_sf) ok = false; }   // :286
+        }
+        if (ok)
+        {
+            const bool o_sf = cand_sf > mean_sf * mult, o_am = cand_am > mean_am * mult;  // :291-292
+            if (type != 0) om = fminf (om, relmarginf (cand_am, mean_am * mult));
+            if (type != 1) om = fminf (om, relmarginf (cand_sf, mean_sf * mult));
+            const bool on = (type == 1) ? o_am : (type == 0 ? o_sf : (type == 2 ? (o_am && o_sf) : false));
+            onset = on ? 1.0f : 0.0f;
+        }
+    }
+    row[FX_ONSET] = onset;
+    if (p.diag) p.diag[(track * p.n_frames + f) * FX_NUM_DIAG + FX_DIAG_ONSET_MARGIN] = om;
+
+    // ---- AudioFeatures::getValue for every slot, after both analyser bodies of frame g -------------------
+    float sm[FX_NUM_FEATURES];
+    const long rec10 = g + 1 < 10 ? g + 1 : 10;
+    for (int k = 0; k < FX_NUM_FEATURES; ++k)
+    {
+        float total = 0.0f;
+        if (k == FX_ONSET)      { total += onset; sm[k] = total / 1.0f; }
+        else if (k == FX_FLUX)  { total += row[FX_FLUX]; sm[k] = total / 1.0f; }         // depth 1 (RealTimeAnalyser.h:73)
+        else if (k == FX_RMS && p.rms_pushes >= 2)
+        {
+            for (long q = g - 4; q <= g; ++q)
+                if (q >= 0) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
+            const long rec = 2 * (g + 1) < 10 ? 2 * (g + 1) : 10;
+            sm[k] = total / (float) (int) rec;
+        }
+        else
+        {
+            for (long q = g - 9; q <= g; ++q)
+                if (q >= 0) total += raw_row (p, track, q)[k];
+            sm[k] = total / (float) (int) rec10;                                          // :84-88
+        }
+    }
+    if (p.smooth)
+    {
+        float* so = p.smooth + (track * p.n_frames + f) * FX_NUM_FEATURES;
+        for (int k = 0; k < FX_NUM_FEATURES; ++k) so[k] = sm[k];
+    }
+    if (p.latest && f == p.n_frames - 1)
+    {
+        float* lo = p.latest + track * (FX_NUM_FEATURES + 2);
+        for (int k = 0; k < FX_NUM_FEATURES; ++k) lo[k] = sm[k];
+        const unsigned long long cnt = (unsigned long long) (g + 1);
+        lo[FX_NUM_FEATURES]     = __uint_as_float ((unsigned) (cnt & 0xffffffffull));
+        lo[FX_NUM_FEATURES + 1] = __uint_as_float ((unsigned) (cnt >> 32));
+    }
+}
+
+__global__ void __launch_bounds__ (128) k_hist (const SmoothParams p, long n_tracks)
+{
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tracks * kHistRows * FX_NUM_FEATURES) return;
+    const int k = (int) (idx % FX_NUM_FEATURES);
+    const int i = (int) ((idx / FX_NUM_FEATURES) % kHistRows);
+    const long track = idx / (FX_NUM_FEATURES * kHistRows);
+    const long j = p.frames_before + p.n_frames - kHistRows + i;
+    float v = 0.0f;
+    if (j >= 0 && j >= p.frames_before - kHistRows) v = raw_row (p, track, j)[k];
+    p.hist_out[(track * kHistRows + i) * FX_NUM_FEATURES + k] = v;
+}
+
+cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t stream)
+{
+    const long total = n_tracks * p.n_frames;
+    if (total > 0)
+    {
+        k_smooth<<<(unsigned) ((total + 127) / 128), 128, 0, stream>>> (p, n_tracks);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const long ht = n_tracks * kHistRows * FX_NUM_FEATURES;
+    k_hist<<<(unsigned) ((ht + 127) / 128), 128, 0, stream>>> (p, n_tracks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011), counter = sample index / 4, key = seed ^ track
+__device__ __forceinline__ void philox4x32_10 (uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out)
+{
+    #pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+        const uint32_t hi0 = __umulhi (0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi (0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__ (256) k_synth (float* audio, long track_stride, long n_samples, long n_tracks,
+                                                 long first_track, double sample_rate, uint64_t seed)
+{
+    const long quads = (n_samples + 3) / 4;
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tracks * quads) return;
+    const long tl = idx / quads;
+    const long n0 = (idx % quads) * 4;
+    const long track = first_track + tl;
+    const uint64_t key = seed ^ (uint64_t) track;
+    uint32_t r[4];
+    philox4x32_10 ((uint32_t) (n0 >> 2), (uint32_t) ((uint64_t) (n0 >> 2) >> 32), 0u, 0u, (uint32_t) key, (uint32_t) (key >> 32), r);
+
+    const int reg = (int) (track & 7);
+    const double sigma = reg == 6 ? 0.5 : (reg == 7 ? 0.001 : 0.05);                      // the three flatness regimes
+    const double freq = 110.0 * exp2 ((double) (track % 48) / 12.0);
+    double ph = (double) track * 0.61803398874989484820;
+    ph -= floor (ph);                                                                     // phi_t / (2 pi)
+    const long sr = (long) sample_rate;
+    float* dst = audio + tl * track_stride;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const long n = n0 + i;
+        if (n >= n_samples) break;
+        const double u = (double) (r[i] >> 8) * (1.0 / 8388608.0) - 1.0;                  // uniform [-1, 1)
+        double x = 0.5 * sinpi (2.0 * (freq * (double) n / sample_rate + ph)) + sigma * u;
+        if ((n % sr) < sr / 20) x *= 4.0;                                                 // burst at the top of every second (onsets)
+        if ((track & 1) && (n % (2 * sr)) >= sr && (n % (2 * sr)) < sr + sr / 4) x = 0.0; // 0.25 s of silence every 2 s on odd tracks
+        dst[n] = (float) x;
+    }
+}
+
+cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
+                          double sample_rate, uint64_t seed, cudaStream_t stream)
+{
+    const long total = n_tracks * ((n_samples + 3) / 4);
+    if (total <= 0) return cudaSuccess;
+    k_synth<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>> (d_audio, track_stride, n_samples, n_tracks, first_track, sample_rate, seed);
+    return cudaGetLastError();
+}
+
+} // namespace fx

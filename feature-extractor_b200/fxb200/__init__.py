@@ -1,0 +1,227 @@
+"""fxb200 -- thin ctypes binding over the C ABI of libfxb200.so (include/fx_engine.h).
+
+This is plumbing for tests and bench.py: the product is the shared library (CUDA kernels for sm_100a behind
+a C ABI) and the C++ facade in ../host/.  There is deliberately no CPU fallback here: if the library is
+missing or no CUDA device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_long, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfxb200.so")
+
+NUM_FEATURES = 12
+NUM_DIAG = 10
+FEATURES = ("onset", "rms", "f0", "centroid", "spread", "flatness", "ler", "flux", "slope", "her", "oer", "inharm")
+DIAG = ("true_oer", "lag", "pitch_margin", "num_peaks", "peak_margin", "flat_count", "flat_margin", "gate_margin",
+        "onset_margin", "flat_state")
+# OSCFeatureAnalysisOutput.h:107 (12 floats on the wire) and README.md:55-57 (10 floats documented)
+OSC_ORDER_CODE = ("onset", "rms", "f0", "centroid", "slope", "spread", "flatness", "ler", "flux", "her", "oer", "inharm")
+OSC_ORDER_README = ("onset", "rms", "f0", "centroid", "slope", "spread", "flatness", "flux", "her", "inharm")
+
+# every symbol include/fx_engine.h declares
+EXPORTS = (
+    "fx_default_config", "fx_engine_create", "fx_engine_destroy", "fx_last_error", "fx_version", "fx_set_gain",
+    "fx_set_onset", "fx_reset", "fx_analyse_host", "fx_analyse_device", "fx_push_block", "fx_process",
+    "fx_poll_features", "fx_flush", "fx_osc_order", "fx_synth_device", "fx_kernel_launches",
+)
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ("n_tracks", c_int), ("window", c_int), ("hop", c_int), ("sample_rate", c_double), ("device", c_int),
+        ("rms_pushes_per_frame", c_int), ("onset_type", c_int), ("onset_hist", c_int), ("onset_multiplier", c_float),
+        ("gain", c_float), ("max_frames_per_call", c_long), ("ring_hops", c_int), ("tracks_per_group", c_int),
+    ]
+
+
+class FxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> ctypes.CDLL:
+    """Load libfxb200.so and declare its prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FxError(f"{p} not found: build it with `make -C feature-extractor_b200` (or __graft_entry__.build()); "
+                      "there is no CPU fallback")
+    lib = ctypes.CDLL(p)
+    lib.fx_default_config.argtypes = [POINTER(Config)]
+    lib.fx_default_config.restype = None
+    lib.fx_engine_create.argtypes = [POINTER(Config), POINTER(c_void_p)]
+    lib.fx_engine_create.restype = c_int
+    lib.fx_engine_destroy.argtypes = [c_void_p]
+    lib.fx_engine_destroy.restype = c_int
+    lib.fx_last_error.argtypes = [c_void_p]
+    lib.fx_last_error.restype = c_char_p
+    lib.fx_version.argtypes = []
+    lib.fx_version.restype = c_char_p
+    lib.fx_set_gain.argtypes = [c_void_p, c_int, c_float]
+    lib.fx_set_gain.restype = c_int
+    lib.fx_set_onset.argtypes = [c_void_p, c_int, c_int, c_int, c_float]
+    lib.fx_set_onset.restype = c_int
+    lib.fx_reset.argtypes = [c_void_p]
+    lib.fx_reset.restype = c_int
+    lib.fx_analyse_host.argtypes = [c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_void_p, POINTER(c_long)]
+    lib.fx_analyse_host.restype = c_int
+    lib.fx_analyse_device.argtypes = [c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_long)]
+    lib.fx_analyse_device.restype = c_int
+    lib.fx_push_block.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), c_int]
+    lib.fx_push_block.restype = c_int
+    lib.fx_process.argtypes = [c_void_p, POINTER(c_long)]
+    lib.fx_process.restype = c_int
+    lib.fx_poll_features.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_uint64)]
+    lib.fx_poll_features.restype = c_int
+    lib.fx_flush.argtypes = [c_void_p]
+    lib.fx_flush.restype = c_int
+    lib.fx_osc_order.argtypes = [POINTER(c_float), POINTER(c_float), c_int]
+    lib.fx_osc_order.restype = c_int
+    lib.fx_synth_device.argtypes = [c_void_p, c_void_p, c_long, c_long, c_long, c_uint64, c_void_p]
+    lib.fx_synth_device.restype = c_int
+    lib.fx_kernel_launches.argtypes = [c_void_p]
+    lib.fx_kernel_launches.restype = c_uint64
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_config(**overrides) -> Config:
+    lib = load_library()
+    cfg = Config()
+    lib.fx_default_config(ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown fx_config field {k!r}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Engine:
+    """One fx_engine: n_tracks analyser tracks on one GPU."""
+
+    def __init__(self, **cfg):
+        self.lib = load_library()
+        self.cfg = default_config(**cfg)
+        self._h = c_void_p()
+        st = self.lib.fx_engine_create(ctypes.byref(self.cfg), ctypes.byref(self._h))
+        if st != 0:
+            raise FxError(f"fx_engine_create failed ({st}): {self.lib.fx_last_error(None).decode()}")
+
+    # -- lifetime ------------------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.lib.fx_engine_destroy(self._h)
+            self._h = c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int, what: str):
+        if st != 0:
+            raise FxError(f"{what} failed ({st}): {self.lib.fx_last_error(self._h).decode()}")
+
+    # -- parameters ----------------------------------------------------------------------------------------
+    def set_gain(self, gain: float, track: int = -1):
+        self._check(self.lib.fx_set_gain(self._h, track, gain), "fx_set_gain")
+
+    def set_onset(self, type: int = 1, hist_len: int = 5, multiplier: float = 1.7, track: int = -1):
+        self._check(self.lib.fx_set_onset(self._h, track, type, hist_len, multiplier), "fx_set_onset")
+
+    def reset(self):
+        self._check(self.lib.fx_reset(self._h), "fx_reset")
+
+    # -- batch analysis, host buffers ------------------------------------------------------------------------
+    def analyse_host(self, audio: np.ndarray, want_raw=True, want_smooth=True, want_diag=True):
+        """audio: float32 [n_tracks, n_samples] (C-contiguous rows).  Returns dict of numpy arrays."""
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        if a.ndim != 2 or a.shape[0] != self.cfg.n_tracks:
+            raise ValueError("audio must be [n_tracks, n_samples]")
+        T, S = a.shape
+        F = S // self.cfg.hop
+        raw = np.empty((T, F, NUM_FEATURES), np.float32) if want_raw else None
+        smooth = np.empty((T, F, NUM_FEATURES), np.float32) if want_smooth else None
+        diag = np.empty((T, F, NUM_DIAG), np.float32) if want_diag else None
+        nf = c_long(0)
+        st = self.lib.fx_analyse_host(self._h, a.ctypes.data, S, S,
+                                      raw.ctypes.data if want_raw else None,
+                                      smooth.ctypes.data if want_smooth else None,
+                                      diag.ctypes.data if want_diag else None, ctypes.byref(nf))
+        self._check(st, "fx_analyse_host")
+        assert nf.value == F
+        return {"raw": raw, "smooth": smooth, "diag": diag, "frames": F}
+
+    def analyse_host_ptr(self, audio_ptr: int, track_stride: int, n_samples: int, raw_ptr=None, smooth_ptr=None, diag_ptr=None) -> int:
+        nf = c_long(0)
+        st = self.lib.fx_analyse_host(self._h, audio_ptr, track_stride, n_samples, raw_ptr, smooth_ptr, diag_ptr, ctypes.byref(nf))
+        self._check(st, "fx_analyse_host")
+        return nf.value
+
+    # -- batch analysis, device buffers (raw pointers; torch is only used by callers for allocation) ----------
+    def analyse_device(self, d_audio_ptr: int, track_stride: int, n_samples: int, d_raw_ptr=None, d_smooth_ptr=None,
+                       d_diag_ptr=None, stream: int | None = None) -> int:
+        nf = c_long(0)
+        st = self.lib.fx_analyse_device(self._h, d_audio_ptr, track_stride, n_samples, d_raw_ptr, d_smooth_ptr,
+                                        d_diag_ptr, stream, ctypes.byref(nf))
+        self._check(st, "fx_analyse_device")
+        return nf.value
+
+    def synth_device(self, d_audio_ptr: int, track_stride: int, n_samples: int, first_track: int = 0, seed: int = 0x5EED,
+                     stream: int | None = None):
+        self._check(self.lib.fx_synth_device(self._h, d_audio_ptr, track_stride, n_samples, first_track, seed, stream),
+                    "fx_synth_device")
+
+    # -- real-time path ----------------------------------------------------------------------------------------
+    def push_block(self, block: np.ndarray, first_track: int = 0):
+        """block: float32 [n_tracks_in_block, n_samples]; row i feeds track first_track + i."""
+        b = np.ascontiguousarray(block, dtype=np.float32)
+        n, s = b.shape
+        ptrs = (c_void_p * n)(*[b.ctypes.data + i * s * 4 for i in range(n)])
+        self._check(self.lib.fx_push_block(self._h, first_track, n, ptrs, s), "fx_push_block")
+
+    def process(self) -> int:
+        nf = c_long(0)
+        self._check(self.lib.fx_process(self._h, ctypes.byref(nf)), "fx_process")
+        return nf.value
+
+    def poll(self, track: int):
+        out = (c_float * NUM_FEATURES)()
+        idx = c_uint64(0)
+        self._check(self.lib.fx_poll_features(self._h, track, out, ctypes.byref(idx)), "fx_poll_features")
+        return np.frombuffer(out, dtype=np.float32).copy(), idx.value
+
+    def flush(self):
+        self._check(self.lib.fx_flush(self._h), "fx_flush")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.fx_kernel_launches(self._h))
+
+
+def osc_order(vec12: np.ndarray, n_out: int = 12) -> np.ndarray:
+    lib = load_library()
+    v = np.ascontiguousarray(vec12, dtype=np.float32)
+    out = np.empty(n_out, np.float32)
+    st = lib.fx_osc_order(v.ctypes.data_as(POINTER(c_float)), out.ctypes.data_as(POINTER(c_float)), n_out)
+    if st != 0:
+        raise FxError(f"fx_osc_order failed ({st})")
+    return out

@@ -1,0 +1,205 @@
+"""Test-side helpers: load the CPU checkers under oracle/, make seeded signals, compare feature blocks.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this module: it is the
+checker, never the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "libfxoracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libfxref.so")
+
+NUM_FEATURES = 12
+NUM_DIAG = 10
+F = {n: i for i, n in enumerate(("onset", "rms", "f0", "centroid", "spread", "flatness", "ler", "flux", "slope", "her", "oer", "inharm"))}
+D = {n: i for i, n in enumerate(("true_oer", "lag", "pitch_margin", "num_peaks", "peak_margin", "flat_count", "flat_margin",
+                                 "gate_margin", "onset_margin", "flat_state"))}
+
+
+class OracleConfig(ctypes.Structure):
+    _fields_ = [("window", ctypes.c_int), ("hop", ctypes.c_int), ("sample_rate", ctypes.c_double), ("gain", ctypes.c_float),
+                ("onset_type", ctypes.c_int), ("onset_hist", ctypes.c_int), ("onset_multiplier", ctypes.c_float),
+                ("rms_pushes", ctypes.c_int), ("mode", ctypes.c_int)]
+
+
+def build_oracle():
+    """(Re)build the C port, and oracle/_ref where /root/reference exists."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True, stdout=subprocess.DEVNULL)
+
+
+class Oracle:
+    def __init__(self, path: str):
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.fxo_default_config.argtypes = [ctypes.POINTER(OracleConfig)]
+        L.fxo_kind.restype = ctypes.c_char_p
+        L.fxo_analyse_track.restype = ctypes.c_long
+        L.fxo_analyse_track.argtypes = [ctypes.POINTER(OracleConfig), ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+        L.fxo_analyse_tracks.restype = ctypes.c_long
+        L.fxo_analyse_tracks.argtypes = [ctypes.POINTER(OracleConfig), ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.c_long,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int]
+        L.fxo_fft_forward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.fxo_fft_inverse.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.kind = L.fxo_kind().decode()
+
+    def config(self, window=2048, hop=1024, sample_rate=48000.0, **kw) -> OracleConfig:
+        c = OracleConfig()
+        self.lib.fxo_default_config(ctypes.byref(c))
+        c.window, c.hop, c.sample_rate = window, hop, sample_rate
+        for k, v in kw.items():
+            if not hasattr(c, k):
+                raise TypeError(k)
+            setattr(c, k, v)
+        return c
+
+    def analyse(self, audio: np.ndarray, threads: int = 0, **cfg):
+        """audio [T, S] float32 -> dict(raw [T,F,12], smooth [T,F,12], diag [T,F,10])"""
+        a = np.ascontiguousarray(np.atleast_2d(audio), dtype=np.float32)
+        c = self.config(**cfg)
+        T, S = a.shape
+        Fr = S // c.hop
+        raw = np.zeros((T, Fr, NUM_FEATURES), np.float32)
+        smooth = np.zeros((T, Fr, NUM_FEATURES), np.float32)
+        diag = np.zeros((T, Fr, NUM_DIAG), np.float32)
+        nthreads = threads or min(T, os.cpu_count() or 1)
+        n = self.lib.fxo_analyse_tracks(ctypes.byref(c), a.ctypes.data, T, S, S, raw.ctypes.data, smooth.ctypes.data,
+                                        diag.ctypes.data, Fr, nthreads)
+        assert n == Fr, (n, Fr)
+        return {"raw": raw, "smooth": smooth, "diag": diag, "frames": Fr}
+
+    def fft_forward(self, frame: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(frame, dtype=np.float32)
+        out = np.zeros(2 * len(x), np.float32)
+        self.lib.fxo_fft_forward(x.ctypes.data, len(x), out.ctypes.data)
+        return out
+
+    def fft_inverse(self, buf2n: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(buf2n, dtype=np.float32).copy()
+        self.lib.fxo_fft_inverse(b.ctypes.data, len(b) // 2)
+        return b
+
+
+def port() -> Oracle:
+    if not os.path.exists(PORT_SO):
+        build_oracle()
+    return Oracle(PORT_SO)
+
+
+def reference() -> Oracle | None:
+    """The reference's own headers compiled headless (prebuilt in this container; travels to the GPU box)."""
+    return Oracle(REF_SO) if os.path.exists(REF_SO) else None
+
+
+def best_oracle() -> Oracle:
+    return reference() or port()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def make_signal(n_samples: int, sr: float, track: int, seed: int = 0x5EED, silence=True, bursts=True) -> np.ndarray:
+    """Seeded sine + uniform noise in the spirit of SURVEY.md section 8d (numpy RNG; the same array is fed to the
+    oracle and to the GPU, so no cross-platform bit-exactness of the generator is needed)."""
+    rng = np.random.default_rng([seed, track])
+    n = np.arange(n_samples, dtype=np.float64)
+    reg = track % 8
+    sigma = 0.5 if reg == 6 else (0.001 if reg == 7 else 0.05)
+    freq = 110.0 * 2.0 ** ((track % 48) / 12.0)
+    phi = 2 * np.pi * ((track * 0.6180339887498949) % 1.0)
+    x = 0.5 * np.sin(2 * np.pi * freq * n / sr + phi) + sigma * rng.uniform(-1.0, 1.0, n_samples)
+    isr = int(sr)
+    if bursts:
+        x[(np.arange(n_samples) % isr) < isr // 20] *= 4.0
+    if silence and (track & 1):
+        m = np.arange(n_samples) % (2 * isr)
+        x[(m >= isr) & (m < isr + isr // 4)] = 0.0
+    return x.astype(np.float32)
+
+
+def make_tracks(n_tracks: int, n_samples: int, sr: float, first_track: int = 0, **kw) -> np.ndarray:
+    return np.stack([make_signal(n_samples, sr, first_track + t, **kw) for t in range(n_tracks)])
+
+
+# ---------------------------------------------------------------------------------------------------------
+TOL = 1e-4          # BASELINE.json north_star: <= 1e-4 on normalised [0, 1] outputs
+MARGIN_TOL = 1e-4   # decisions whose relative margin is below this are exempt (and counted)
+
+
+def close(a: np.ndarray, b: np.ndarray, tol: float = TOL) -> np.ndarray:
+    """Element-wise parity: inf/NaN by class, otherwise |a - b| <= tol * max (1, |b|)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    fin = np.isfinite(a) & np.isfinite(b)
+    with np.errstate(invalid="ignore"):
+        ok = fin & (np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
+    return ok | both_nan | both_inf
+
+
+def compare(gpu: dict, ora: dict, tol: float = TOL, margin_tol: float = MARGIN_TOL, smooth_halo: int = 10) -> dict:
+    """Compare GPU and oracle feature blocks frame by frame.
+
+    A raw mismatch is EXEMPT when a decision that feeds the value had a relative margin below margin_tol on
+    either side (pitch lag -> f0/her/oer/inharm; peak set -> inharm; flatness gate; silence gates -> everything;
+    onset comparisons).  Smoothed values are exempt for smooth_halo frames after an exempt raw frame.
+    Returns counts; 'bad_raw' / 'bad_smooth' must be zero for parity.
+    """
+    graw, oraw = gpu["raw"], ora["raw"]
+    gd, od = gpu["diag"], ora["diag"]
+
+    def m(name):   # smallest margin seen on either side (oracle/_ref reports -1 for margins it cannot observe)
+        g = gd[..., D[name]]
+        o = od[..., D[name]]
+        o = np.where(o < 0, np.inf, o)
+        return np.minimum(g, o)
+
+    low_pitch = m("pitch_margin") < margin_tol
+    low_peak = m("peak_margin") < margin_tol
+    low_flat = m("flat_margin") < margin_tol
+    low_gate = m("gate_margin") < margin_tol
+    low_onset = m("onset_margin") < margin_tol
+
+    ok = close(graw, oraw, tol)
+    exempt = np.zeros_like(ok)
+    for name in ("f0", "her", "oer", "inharm"):
+        exempt[..., F[name]] |= low_pitch
+    exempt[..., F["inharm"]] |= low_peak
+    exempt[..., F["flatness"]] |= low_flat
+    exempt |= low_gate[..., None]
+    # a flipped gate on the previous non-silent decision changes which spectrum flux is measured against
+    exempt[..., F["flux"]] |= low_gate
+    exempt[..., F["onset"]] |= low_onset
+    bad_raw = ~ok & ~exempt
+
+    # lag must match exactly unless exempt
+    lag_mismatch = (gd[..., D["lag"]] != od[..., D["lag"]])
+    bad_lag = lag_mismatch & ~low_pitch & ~low_gate
+
+    res = {
+        "frames": int(ok.shape[0] * ok.shape[1]),
+        "raw_mismatch_total": int((~ok).sum()),
+        "raw_mismatch_exempt": int((~ok & exempt).sum()),
+        "bad_raw": int(bad_raw.sum()),
+        "lag_mismatch": int(lag_mismatch.sum()),
+        "bad_lag": int(bad_lag.sum()),
+        "low_margin_frames": int((low_pitch | low_peak | low_flat | low_gate | low_onset).sum()),
+    }
+    if gpu.get("smooth") is not None and ora.get("smooth") is not None:
+        oks = close(gpu["smooth"], ora["smooth"], tol)
+        # any raw mismatch (exempt or not) contaminates the next smooth_halo frames of that feature; onset feeds on RMS
+        dirty = ~ok
+        dirty[..., F["onset"]] |= low_onset
+        halo = np.zeros_like(dirty)
+        for k in range(min(smooth_halo + 6, dirty.shape[1])):
+            halo[:, k:, :] |= dirty[:, : dirty.shape[1] - k, :] if k else dirty
+        bad_s = ~oks & ~halo
+        res["smooth_mismatch_total"] = int((~oks).sum())
+        res["bad_smooth"] = int(bad_s.sum())
+    return res
