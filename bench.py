@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- analysed frames/sec of the per-frame analysis hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[2], the one the metric's >= 1e6 frames/s/GPU target is quoted on): 4096 tracks per
+GPU, 4096-point frames, hop 1024, 48 kHz, 10 s of synthetic sine + noise per track (468 frames/track, 1.92 M
+frames and 7.9 GB of fp32 audio per GPU per step -- far larger than L2, so no L2 flush is needed between steps).
+A "step" analyses the next 10 s of every track: K1 k_analyse (framing, 3 FFTs, all features) + K2 flux fix-up
++ K3 smoothing/onset, all 12 features for every frame.  Tracks shard by range across GPUs with no collective
+(weak scaling: 4096 tracks per GPU); torch.distributed is used only for the barrier and the max-over-ranks time.
+
+  value  device-resident throughput (inputs already in HBM), CUDA events on the launching stream, max over ranks
+  e2e    the same metric through the C-ABI call with HOST buffers (fx_analyse_host: pinned host audio in, smoothed
+         features back out, copies inside the timed region)
+  roofline      the binding roofline per BASELINE.json north_star: algorithmic FLOPs/frame (SURVEY.md 8d:
+                10 N log2 N + 48 N) x frames / live-measured k_analyse time vs an FP32 FMA microbenchmark on this GPU
+  roofline_hbm  algorithmic bytes/frame (4 H + 40) x frames / the same time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own analysis classes (oracle/_ref, compiled headless) on this box's host cores,
+                bounded sample of the same workload
+
+`--impl reference` times only that CPU path (all host threads), same metric / config / unit.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "feature-extractor_b200"), os.path.join(ROOT, "tests")]
+
+WINDOW, HOP, SR = 4096, 1024, 48000.0
+METRIC = "analysed frames/sec"
+UNIT = "frames/s"
+
+
+def algorithmic_bytes_per_frame(hop: int) -> float:
+    return 4.0 * hop + 4.0 * 10            # each input sample once + the 10-float feature vector
+
+
+def algorithmic_flops_per_frame(n: int) -> float:
+    return 10.0 * n * math.log2(n) + 48.0 * n   # four real N-point transforms + O(N) feature work
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "BASELINE configs[2]: 4096-track batch, 4096-pt frames, hop 1024, 48 kHz, all 12 features per frame",
+        "tracks_per_gpu": args.tracks, "tracks_total": args.tracks * n_gpus, "seconds_per_track": args.seconds,
+        "window": WINDOW, "hop": HOP, "sample_rate": SR, "frames_per_track": int(SR * args.seconds) // HOP,
+        "parallelism": f"track-range sharding x{n_gpus}, no collective",
+        "l2": "inputs (7.9 GB/GPU/step) exceed L2; no flush needed",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(audio_np, threads: int):
+    """frames/s of the CPU checker on audio_np [T, S]; prefers oracle/_ref (the reference's own classes)."""
+    import oracle_util as ou
+
+    ora = ou.best_oracle()
+    t0 = time.perf_counter()
+    r = ora.analyse(audio_np, threads=threads, window=WINDOW, hop=HOP, sample_rate=SR)
+    dt = time.perf_counter() - t0
+    frames = audio_np.shape[0] * r["frames"]
+    return frames / dt, ora.kind, frames, dt
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle_util as ou
+
+    cores = os.cpu_count() or 1
+    n_tracks = max(2 * cores, 16)
+    seconds = min(args.seconds, 4.0)
+    S = (int(SR * seconds) // HOP) * HOP
+    audio = ou.make_tracks(n_tracks, S, SR)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(audio[: max(cores // 2, 1)], cores)
+    rates, kind = [], "port"
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        rate, kind, frames, dt = cpu_reference_rate(audio, cores)
+        rates.append(rate)
+    total_dt = time.perf_counter() - t_all
+    value = (n_tracks * (S // HOP) * args.steps) / total_dt
+    sample = f"{n_tracks} tracks x {seconds:g} s ({n_tracks * (S // HOP)} frames) per step, {cores} threads over contiguous track ranges"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=4096, help="tracks per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0, help="seconds of audio per track per step")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import fxb200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the analysis path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    T = args.tracks
+    S = (int(SR * args.seconds) // HOP) * HOP
+    F = S // HOP
+    frames_per_step = T * F
+
+    eng = fxb200.Engine(n_tracks=T, window=WINDOW, hop=HOP, sample_rate=SR, device=local_rank)
+    # a non-default stream: its handle is non-zero, so the library launches on exactly the stream the events are recorded on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+    audio = torch.empty((T, S), dtype=torch.float32, device=dev)
+    raw = torch.empty((T, F, 12), dtype=torch.float32, device=dev)
+    smooth = torch.empty((T, F, 12), dtype=torch.float32, device=dev)
+    eng.synth_device(audio.data_ptr(), S, S, first_track=rank * T, stream=sptr)
+    torch.cuda.synchronize(dev)
+
+    def step():
+        eng.analyse_device(audio.data_ptr(), S, S, raw.data_ptr(), smooth.data_ptr(), None, stream=sptr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # FP32 peak (registers-only FMA loop) for the compute roofline, measured on this GPU before the timed region
+    fp32_peak = fxb200.measure_fp32_peak(local_rank)
+
+    eng.profile_enable(True)
+    eng.profile_read()
+    launches0 = eng.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches - launches0
+    ms_k1, ms_post, ncalls = eng.profile_read()
+    eng.profile_enable(False)
+
+    t_local = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_max = float(t_local.item())
+    value = frames_per_step * world * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_audio = torch.empty((T, S), dtype=torch.float32, pin_memory=True)
+        h_audio.copy_(audio)
+        h_smooth = torch.empty((T, F, 12), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize(dev)
+        eng.analyse_host_ptr(h_audio.data_ptr(), S, S, None, h_smooth.data_ptr(), None)       # warm-up (allocates the pipeline slots)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.analyse_host_ptr(h_audio.data_ptr(), S, S, None, h_smooth.data_ptr(), None)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": frames_per_step * world * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": T * S * 4 * world, "d2h_bytes_per_step": T * F * 12 * 4 * world,
+               "steps": args.e2e_steps, "api": "fx_analyse_host (pinned host audio in, smoothed features out)"}
+        del h_audio, h_smooth
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cpu_tracks = min(T, max(4 * cores, 32))
+        sample_audio = audio[:n_cpu_tracks].cpu().numpy()
+        rate, kind, frames, dt = cpu_reference_rate(sample_audio, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {n_cpu_tracks} tracks x {args.seconds:g} s of the same device-synthesised workload ({frames} frames, {dt:.1f} s wall, {cores} threads)"}
+
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        k1_s = (ms_k1 * 1e-3) / max(ncalls, 1)                       # average k_analyse launch duration, CUDA events on its stream
+        flops = algorithmic_flops_per_frame(WINDOW) * frames_per_step
+        byts = algorithmic_bytes_per_frame(HOP) * frames_per_step
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, world),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "k_analyse<16>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": None,
+                         "peak_source": "FMA microbenchmark on this GPU (fx_measure_fp32_peak), measured",
+                         "note": "binding roofline per north_star: min (HBM_BW / B, FP32_peak / F) is the FP32 term for this path",
+                         "kernel_ms": k1_s * 1e3, "kernel_share_of_step": ms_k1 / ms_total if ms_total else None},
+            "roofline_hbm": {"bound": "hbm", "kernel": "k_analyse<16>", "achieved": byts / k1_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": byts / k1_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

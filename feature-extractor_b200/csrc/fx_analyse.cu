@@ -1,4 +1,4 @@
-// fx_analyse.cu -- K1, the per-frame analysis kernel (sm_100a).
+// fx_analyse.cu -- K1, the per-frame analysis kernel (sm_100a), and K1b, the per-frame finalisation.
 //
 // One CTA walks a chunk of consecutive frames of one track.  Per frame it reproduces, on the GPU, the two
 // analyser bodies of the reference (all citations relative to /root/reference/Source/):
@@ -10,10 +10,15 @@
 //
 // Data movement: the hop's new samples arrive by cp.async.bulk (TMA bulk copy, mbarrier completion) into a
 // shared-memory ring holding the N-sample window, so each input sample crosses HBM once per chunk; the next
-// hop is prefetched while the current frame's FFTs run.  Three complex FFTs per frame:
+// hop is prefetched while the current frame's FFTs run.  Three complex FFTs per frame, all through ONE
+// out-of-line copy of the FFT code (the kernel is instruction-cache bound otherwise):
 //   FFT1  z = x + i (x * w)      -> Re A (raw frame), Re B / Im B (windowed frame) by conjugate symmetry
 //   FFT2  c = onepole (x) * w    -> P[k] = Re C[k]^2
-//   FFT3  inverse of P (chained in registers from FFT2) -> d[s], only the real part is used (PitchAnalyser.h:163)
+//   FFT3  forward transform of the real sequence P, chained in registers from FFT2: its real part equals the
+//         real part of the inverse transform the reference performs (PitchAnalyser.h:120), which is all that
+//         can reach the lag search (PitchAnalyser.h:163)
+// K1 leaves the per-frame sums in a FrameRec; K1b (one thread per frame) applies the scalar tail of the
+// reference (pow / log10 / sqrt, clamps, gates) so that no serial libm code sits inside the frame loop.
 // All feature reductions accumulate in fp64 like the reference.  No tensor cores: nothing here is a GEMM.
 #include "fx_fft.cuh"
 #include "fx_kernels.cuh"
@@ -60,22 +65,59 @@ __device__ __forceinline__ void fence_proxy_async()
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// small numeric helpers
-__device__ __forceinline__ float relmargin (double a, double b)
+// small numeric helpers.  Margins are diagnostics: fp32 with the fast reciprocal is plenty.
+__device__ __forceinline__ float relmargin_f (float a, float b)
 {
-    const double m = fmax (fabs (a), fabs (b));
-    return (m > 0.0) ? (float) (fabs (a - b) / m) : 0.0f;
+    const float m = fmaxf (fabsf (a), fabsf (b));
+    return (m > 0.0f) ? __fdividef (fabsf (a - b), m) : 0.0f;
+}
+__device__ __forceinline__ float relmargin_d (double a, double b)
+{
+    const float m = (float) fmax (fabs (a), fabs (b));
+    return (m > 0.0f) ? __fdividef ((float) fabs (a - b), m) : 0.0f;
+}
+// margin of a comparison between cnd values with fp32 uncertainties ua, ub (see estimate_pitch in oracle/fx_oracle.c)
+__device__ __forceinline__ float noisy_margin (float a, float ua, float b, float ub)
+{
+    const float gap = fabsf (a - b) - (ua + ub);
+    const float m = fmaxf (fabsf (a), fabsf (b));
+    return (gap > 0.0f && m > 0.0f) ? __fdividef (gap, m) : 0.0f;
 }
 
-// extended-range product: value = m * 2^e with m in [0.5, 1)
+// Conservative (never over-estimating) relative gap between two non-negative fp32 values from the distance of
+// their bit patterns: |a - b| / max (a, b) >= ulps * 2^-24.  Three integer instructions per comparison.
+__device__ __forceinline__ unsigned ulp_gap (float a, float b)
+{
+    const int d = (int) __float_as_uint (a) - (int) __float_as_uint (b);
+    return (unsigned) (d < 0 ? -d : d);
+}
+__device__ __forceinline__ float ulps_to_margin (unsigned u)
+{
+    return u >= (1u << 24) ? 1.0f : (float) u * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
+{
+    return (m * 2.0) * __hiloint2double ((e - 1 + 1023) << 20, 0);
+}
+
+// extended-range product of fp64 magnitudes: value = m * 2^e with m in [0.5, 1).  Inputs are squares of fp32
+// values, i.e. normal doubles, so the exponent field can be read directly.
 struct ME { double m; int e; };
 __device__ __forceinline__ ME me_one() { ME r; r.m = 0.5; r.e = 1; return r; }
-__device__ __forceinline__ ME me_from (double x) { ME r; r.m = frexp (x, &r.e); return r; }
+__device__ __forceinline__ ME me_from (double x)
+{
+    ME r;
+    const int hi = __double2hiint (x);
+    r.e = ((hi >> 20) & 0x7ff) - 1022;
+    r.m = __hiloint2double ((hi & 0x800fffff) | 0x3fe00000, __double2loint (x));
+    return r;
+}
 __device__ __forceinline__ ME me_mul (ME a, ME b)
 {
-    ME r; int ex;
-    r.m = frexp (a.m * b.m, &ex);
-    r.e = a.e + b.e + ex;
+    ME r;
+    r.m = a.m * b.m;                     // in [0.25, 1)
+    r.e = a.e + b.e;
+    if (r.m < 0.5) { r.m *= 2.0; r.e -= 1; }
     return r;
 }
 
@@ -98,6 +140,12 @@ __device__ __forceinline__ float warp_minf (float v)
     for (int off = 16; off > 0; off >>= 1) v = fminf (v, __shfl_xor_sync (0xffffffffu, v, off));
     return v;
 }
+__device__ __forceinline__ float warp_maxf (float v)
+{
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf (v, __shfl_xor_sync (0xffffffffu, v, off));
+    return v;
+}
 __device__ __forceinline__ unsigned warp_minu (unsigned v)
 {
     #pragma unroll
@@ -116,9 +164,9 @@ template <int R1> struct Smem
 {
     using D = FftDims<R1>;
     static constexpr int N = D::N, M = N / 2, T = D::T, NW = T / 32;
-    static constexpr int kRed = 12;
+    static constexpr int kRed = 10;
 
-    float2   ex[D::EX_LEN];          // FFT exchange buffer; doubles as the fp32 work array (skewed, N*17/16 floats)
+    float2   ex[D::EX_LEN];          // FFT exchange buffer; doubles as two fp32 work arrays (skewed, N*17/16 floats each)
     float2   tw1[D::TW1_LEN];
     float2   tw2[D::TW2_LEN];
     float    ring[N];                // ring[a & (N-1)] = absolute sample a of the track
@@ -133,10 +181,31 @@ template <int R1> struct Smem
     float    fmins[2][NW];
     double   flat_prod;
     double   f0;
+    float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     float    her_terms[18];
     int      her_bins[18];
     uint64_t mbar;
 };
+
+extern __shared__ __align__ (128) unsigned char fx_smem_raw[];
+
+struct V16 { float2 v[16]; };
+
+// The one copy of the FFT: stage 1 (+ twiddle) -> exchange -> stage 2 (+ twiddle) -> exchange -> stage 3.
+// v: slot q * R1 + n1 = input n1 of stage-1 butterfly m0 + T q.  Returns slot s = X[klow (t) + T * out_index<16> (s)].
+// The caller guarantees the exchange buffer is free on entry; on return other threads may still be reading it.
+template <int R1>
+__device__ __noinline__ V16 fft_core (V16 io, int m0)
+{
+    Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
+    const int t = threadIdx.x;
+    fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1);
+    __syncthreads();
+    fft_stage2<R1, false> (t, sm.ex, sm.tw2);
+    __syncthreads();
+    fft_stage3<R1, false> (t, sm.ex, io.v);
+    return io;
+}
 
 template <int R1>
 __global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 2 : (R1 == 8 ? 4 : 8)))
@@ -146,9 +215,9 @@ k_analyse (const AnalyseParams p)
     using S = Smem<R1>;
     constexpr int N = D::N, M = N / 2, T = D::T, NW = T / 32, Q1 = D::Q1;
 
-    extern __shared__ __align__ (128) unsigned char smem_raw[];
-    S& sm = *reinterpret_cast<S*> (smem_raw);
-    float* workf = reinterpret_cast<float*> (sm.ex);
+    S& sm = *reinterpret_cast<S*> (fx_smem_raw);
+    float* workf = reinterpret_cast<float*> (sm.ex);          // fp32 view, skewed index phys (n)
+    float* workg = workf + D::EX_LEN;                          // second fp32 array in the same buffer
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long cta = blockIdx.x;
@@ -158,7 +227,7 @@ k_analyse (const AnalyseParams p)
     const int f_end = min (p.n_frames, f_begin + p.frames_per_chunk);
     if (f_begin >= f_end)
     {
-        if (t == 0 && f_begin < p.n_chunks * p.frames_per_chunk) p.first_idx[track * p.n_chunks + chunk] = -1;
+        if (t == 0) p.first_idx[track * p.n_chunks + chunk] = -1;
         return;
     }
 
@@ -188,8 +257,8 @@ k_analyse (const AnalyseParams p)
             const float* g = nullptr;
             if (j >= p.first_hop)                  g = src + (j - p.first_hop) * H;
             else if (j >= 0)                       g = tail + (j - (p.first_hop - (NB - 1))) * H;
-            if (g == nullptr)      { for (int i = t; i < H; i += T) dst[i] = 0.0f; }      // before the stream started (RealTimeAudioAnalysis.h:202)
-            else if (! p.use_bulk) { for (int i = t; i < H; i += T) dst[i] = g[i]; }
+            if (g == nullptr)      { _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = 0.0f; }      // before the stream started (RealTimeAudioAnalysis.h:202)
+            else if (! p.use_bulk) { _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = g[i]; }
             else                   bulk_bytes += (uint32_t) H * 4u;
         }
         if (p.use_bulk && t == 0)
@@ -212,23 +281,24 @@ k_analyse (const AnalyseParams p)
     int cur = 0;                      // specB[cur] receives this frame, specB[cur ^ 1] is the previous non-silent frame
     bool have_prev = false;           // false until the chunk's first non-silent frame (its flux is fixed up by K2)
     int first_nonsilent = -1;
-    const float max_flux = (float) (M * (M + 1)) / 2.0f;            // SpectralCharacteristics.h:111
-    const int lower_portion = M / 5;                                // :65
+    const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
+    const int b0 = 8 * t;                                           // this thread's 8 consecutive bins
+    const double inv_m = 1.0 / (double) M;                          // exact: M is a power of two
 
+    #pragma unroll 1
     for (int f = f_begin; f < f_end; ++f)
     {
         const long j_new = p.first_hop + f;
         const long a0 = (j_new - (NB - 1)) * (long) H;              // absolute sample index of window sample 0
-        float* out = p.raw + (track * p.n_frames + f) * FX_NUM_FEATURES;
-        float* dg  = p.diag ? p.diag + (track * p.n_frames + f) * FX_NUM_DIAG : nullptr;
+        FrameRec* rec = p.rec + (track * p.n_frames + f);
 
         mbar_wait (&sm.mbar, phase);
         phase ^= 1u;
 
         // =========================== FFT1: z = x + i (x * bartlett) ====================================
-        float2 v[16];
-        double rms_part = 0.0;
+        V16 io;
         {
+            double rms_part = 0.0;
             #pragma unroll
             for (int q = 0; q < Q1; ++q)
                 #pragma unroll
@@ -238,31 +308,25 @@ k_analyse (const AnalyseParams p)
                     const float x = __fmul_rn (sm.ring[(int) ((a0 + n) & (N - 1))], gain);       // AudioDataCollector.h:88
                     // RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N (exact in fp32)
                     const float w = (n < M) ? (float) n * (2.0f / N) : 1.0f - (float) (n - M) * (2.0f / N);
-                    v[q * R1 + n1] = make_float2 (x, __fmul_rn (x, w));
+                    io.v[q * R1 + n1] = make_float2 (x, __fmul_rn (x, w));
                     rms_part += (double) __fmul_rn (x, x);                                       // getRMSLevel: fp32 square, fp64 sum
                 }
-        }
-        fft_stage1_store<R1, false> (v, t, sm.ex, sm.tw1);
-        {
             double r1[1] = { rms_part };
             warp_sum<1> (r1);
             if (lane == 0) sm.red[0][0][warp] = r1[0];
         }
-        __syncthreads();                                                                          // (1)
-        fft_stage2<R1, false> (t, sm.ex, sm.tw2);
-        __syncthreads();                                                                          // (2)
-        fft_stage3<R1, false> (t, sm.ex, v);
-        __syncthreads();                                                                          // (3)
+        io = fft_core<R1> (io, t);
+        __syncthreads();                                            // every stage-3 read is done: store X in natural order
         {
             const int kl = klow<R1> (t);
             #pragma unroll
-            for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = v[s];
+            for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = io.v[s];
         }
-        __syncthreads();                                                                          // (4)
+        __syncthreads();
 
         // split the packed spectrum: A = FFT (x), B = FFT (x w); keep Re A, Re B; Im B only for the slope quirk
         float rawmax = 0.0f;     // SpectralCharacteristics.h:153: max |buf[j]|, j < M, over the interleaved Re/Im floats = bins k < M/2
-        #pragma unroll
+        #pragma unroll 4
         for (int j = 0; j < 8; ++j)
         {
             const int k = t + T * j;
@@ -275,7 +339,7 @@ k_analyse (const AnalyseParams p)
             sm.specB[cur][k] = reB;
             if (k < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
         }
-        __syncthreads();                                                                          // (5)
+        __syncthreads();
 
         // RMS (RealTimeAnalyser.h:207-208)
         double rms_sum = 0.0;
@@ -286,18 +350,18 @@ k_analyse (const AnalyseParams p)
         const double eps = 0.01 * (double) log_rms;                                               // SpectralCharacteristics.h:108
 
         // =========================== spectral features, pass 1 ========================================
-        double mag[8];
-        const int b0 = 8 * t;
+        float cr[8];
         ME lprod = me_one();
         {
             const float4 c0 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0]);
             const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0 + 4]);
             const float4 p0 = *reinterpret_cast<const float4*> (&sm.specB[cur ^ 1][b0]);
             const float4 p1 = *reinterpret_cast<const float4*> (&sm.specB[cur ^ 1][b0 + 4]);
-            const float cr[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+            cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
-            float fmargin = 1.0f;
+            unsigned fgap = 0xffffffffu;
+            const float eps_f = (float) eps;
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
@@ -307,7 +371,6 @@ k_analyse (const AnalyseParams p)
                 const double pm = (double) pr[j] * (double) pr[j];
                 const double diff = mg - pm;                                                     // :76-79
                 if (diff > 0.0) flux += diff;
-                mag[j] = mg;
                 mag_sum += mg;
                 if (bin <= lower_portion) lhr += mg;                                             // :86-87
                 if (mg > eps)                                                                    // :89-94
@@ -316,7 +379,7 @@ k_analyse (const AnalyseParams p)
                     count += 1.0;
                     lprod = me_mul (lprod, me_from (mg));
                 }
-                fmargin = fminf (fmargin, relmargin (mg, eps));
+                fgap = min (fgap, ulp_gap ((float) mg, eps_f));
                 const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
                 weighted += fc * mg;
                 maxmag = fmax (maxmag, mg);
@@ -324,8 +387,8 @@ k_analyse (const AnalyseParams p)
             double s6[6] = { mag_sum, weighted, flux, lhr, flat_sum, count };
             warp_sum<6> (s6);
             const double wmax = warp_max (maxmag);
-            const double wraw = warp_max ((double) rawmax);
-            const float wmar = warp_minf (fmargin);
+            const float wraw = warp_maxf (rawmax);
+            const float wmar = ulps_to_margin (warp_minu (fgap));
             // inclusive warp scan of the extended-range product, in bin order
             ME inc = lprod;
             #pragma unroll
@@ -343,21 +406,22 @@ k_analyse (const AnalyseParams p)
                 #pragma unroll
                 for (int k = 0; k < 6; ++k) sm.red[1][k][warp] = s6[k];
                 sm.red[1][6][warp] = wmax;
-                sm.red[1][7][warp] = wraw;
                 sm.fmins[0][warp] = wmar;
+                sm.fmins[1][warp] = wraw;
             }
         }
-        __syncthreads();                                                                          // (6)
-        double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0, rawmax_d = 0.0;
-        float flat_margin = 1.0f;
+        __syncthreads();
+        double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
+        float flat_margin = 1.0f, rawmax_all = 0.0f;
         ME total = me_one(), prefix = me_one();
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
             mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w]; flux += sm.red[1][2][w];
             lhr += sm.red[1][3][w]; flat_sum += sm.red[1][4][w]; count += sm.red[1][5][w];
-            maxmag = fmax (maxmag, sm.red[1][6][w]); rawmax_d = fmax (rawmax_d, sm.red[1][7][w]);
+            maxmag = fmax (maxmag, sm.red[1][6][w]);
             flat_margin = fminf (flat_margin, sm.fmins[0][w]);
+            rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
             ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w];
             if (w < warp) prefix = me_mul (prefix, wt);
             total = me_mul (total, wt);
@@ -365,32 +429,33 @@ k_analyse (const AnalyseParams p)
         prefix = me_mul (prefix, lprod);
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
         const float centroid = (float) (weighted / mag_sum);                                      // :127
-        const double max_e = fmax (rawmax_d, maxmag);                                             // :153-163
-        const bool slope_gated = ! (max_e > 0.0001);                                              // :165-167
+        const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
+        const double inv_max_e = 1.0 / max_e;
 
         // =========================== pass 2: spread, slope sums, flatness range events ================
         unsigned ev_code = 0xffffffffu;
-        double ev_before = 1.0;
+        ME ev_run = me_one();
         {
             double var = 0.0, se = 0.0, sie = 0.0;
+            const double cn = (double) centroid / nyquist;                                        // :137
             ME run = prefix;
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
                 const int bin = b0 + j;
-                const double fc = (double) bin * frpb + (frpb / 2.0);
-                const double dv = (fc / nyquist) - ((double) centroid / nyquist);                 // :137
-                var += (dv * dv) * mag[j];
-                const double e = mag[j] / max_e;                                                  // :172
+                const double mg = (double) cr[j] * (double) cr[j];
+                const double dv = ((double) bin + 0.5) * inv_m - cn;                              // fc / nyquist = (bin + 1/2) / M
+                var += (dv * dv) * mg;
+                const double e = mg * inv_max_e;                                                  // :172
                 se += e;
                 sie += (double) bin * e;                                                          // :175
-                if (mag[j] > eps)
+                if (mg > eps)
                 {
-                    const ME nxt = me_mul (run, me_from (mag[j]));
+                    const ME nxt = me_mul (run, me_from (mg));
                     if (ev_code == 0xffffffffu && (nxt.e >= 1025 || nxt.e <= -1022))
                     {
                         ev_code = (unsigned) bin * 2u + (nxt.e >= 1025 ? 1u : 0u);
-                        ev_before = ldexp (run.m, run.e);
+                        ev_run = run;
                     }
                     run = nxt;
                 }
@@ -404,7 +469,7 @@ k_analyse (const AnalyseParams p)
                 sm.ucodes[0][warp] = wev;
             }
         }
-        __syncthreads();                                                                          // (7)
+        __syncthreads();
         double var = 0.0, se = 0.0, sie = 0.0;
         unsigned ev = 0xffffffffu;
         #pragma unroll
@@ -413,12 +478,12 @@ k_analyse (const AnalyseParams p)
             var += sm.red[0][1][w]; se += sm.red[0][2][w]; sie += sm.red[0][3][w];
             ev = min (ev, sm.ucodes[0][w]);
         }
-        const double mean_e = se / (double) M;                                                    // :177
+        const double mean_e = se * inv_m;                                                         // :177
         {
             // pass 3: energy variance (:182-190)
             double evar = 0.0;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { const double d = mag[j] / max_e - mean_e; evar += d * d; }
+            for (int j = 0; j < 8; ++j) { const double d = (double) cr[j] * (double) cr[j] * inv_max_e - mean_e; evar += d * d; }
             double s1[1] = { evar };
             warp_sum<1> (s1);
             if (lane == 0) sm.red[1][0][warp] = s1[0];
@@ -430,7 +495,8 @@ k_analyse (const AnalyseParams p)
                 if (ev & 1u) prod = INFINITY;
                 else
                 {
-                    prod = ev_before;
+                    prod = ldexp_normal (ev_run.m, ev_run.e);
+                    #pragma unroll 1
                     for (int b = (int) (ev >> 1); b < M; ++b)
                     {
                         const double re = (double) sm.specB[cur][b];
@@ -445,93 +511,50 @@ k_analyse (const AnalyseParams p)
                 sm.flat_prod = prod;
             }
         }
-        __syncthreads();                                                                          // (8)
-        if (t == 0)
+        if (! silent && ! have_prev)
         {
-            double evar = 0.0;
-            #pragma unroll
-            for (int w = 0; w < NW; ++w) evar += sm.red[1][0][w];
-            float gate_margin = fminf (relmargin (mag_sum, 0.05), relmargin (max_e, 0.0001));
-            float o_centroid = 0.0f, o_spread = 0.0f, o_flat = 0.0f, o_ler = 0.0f, o_flux = 0.0f, o_slope = 0.0f;
-            float flat_state = 3.0f;
-            if (! silent)
-            {
-                double product;
-                if (ev == 0xffffffffu) { product = ldexp (total.m, total.e); flat_state = 0.0f; }
-                else
-                {
-                    product = sm.flat_prod;
-                    flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f);
-                }
-                const double inv = 1.0 / (count > 0.0 ? count : 1.0);                             // :130
-                const float flat = flat_sum > eps ? (float) (pow (product, inv) / (inv * flat_sum)) : 0.0f;    // :57-60
-                o_flat = (float) log10 ((double) flat * 9.0 + 1.0);                               // :132
-                const float c = __fdiv_rn (centroid, (float) (nyquist / 2.0));                    // :133
-                o_centroid = (float) log10 ((double) __fadd_rn (__fmul_rn (c, 9.0f), 1.0f));      // :134
-                const float max_spread = (float) (((double) centroid / nyquist) * (1.0 - ((double) centroid / nyquist)));   // :140
-                o_spread = (float) ((var / mag_sum) / (double) max_spread);                       // :141
-                o_ler = (float) (lhr / mag_sum);                                                  // :125
-                o_flux = have_prev ? (float) (flux / (double) max_flux) : 0.0f;                   // :112 (K2 fixes the chunk's first non-silent frame)
-            }
-            if (! slope_gated)
-            {
-                const double energy_var = evar / (double) M;
-                const double bin_std = sqrt (p.bin_var), energy_std = sqrt (energy_var);
-                const double r = (sie - ((double) M * mean_e * 0.5)) / (double) ((float) M - 1.0f) * energy_std * bin_std;   // :195
-                o_slope = (float) (r * (bin_std / energy_std));                                   // :198
-            }
-            out[FX_RMS] = log_rms;
-            out[FX_CENTROID] = o_centroid; out[FX_SPREAD] = o_spread; out[FX_FLATNESS] = o_flat;
-            out[FX_LER] = o_ler; out[FX_FLUX] = o_flux; out[FX_SLOPE] = o_slope; out[FX_ONSET] = 0.0f;
-            if (dg)
-            {
-                dg[FX_DIAG_FLAT_COUNT] = (float) count;
-                dg[FX_DIAG_FLAT_MARGIN] = flat_margin;
-                dg[FX_DIAG_FLAT_STATE] = flat_state;
-                dg[FX_DIAG_GATE_MARGIN] = gate_margin;
-                dg[FX_DIAG_ONSET_MARGIN] = 1.0f;
-            }
-        }
-        if (! silent)
-        {
-            if (! have_prev)
-            {
-                have_prev = true;
-                first_nonsilent = f;
-                float* fs = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
-                for (int i = t; i < M; i += T) fs[i] = sm.specB[cur][i];
-            }
-            cur ^= 1;                                                                             // :138 prev <- current
+            float* fs = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
+            *reinterpret_cast<float4*> (&fs[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);
+            *reinterpret_cast<float4*> (&fs[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
         }
 
         // =========================== one-pole filter + window -> work array ============================
         // AudioFilter::filterAudio (RealTimeAudioAnalysis.h:106-125): y[0] = x[0]; y[n] = (pi/2) x[n] + e^(-pi/2) y[n-1].
         // Each thread owns 16 consecutive samples; the recurrence is warmed up over the 16 samples before them
-        // (e^(-pi/2)^16 = 1.2e-11 of the state survives, far below fp32 resolution), then run in the reference's arithmetic.
+        // (e^(-pi/2)^16 = 1.2e-11 of the state survives, far below fp32 resolution), then run in the reference's
+        // arithmetic.  The work array is free: the spectrum split was the last reader of the exchange buffer.
         {
             const int n0 = 16 * t;
-            float y = 0.0f;
-            if (t > 0)
+            const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
+            float xs[16];
+            #pragma unroll
+            for (int q = 0; q < 4; ++q)
             {
-                const int w0 = n0 - 16;
-                #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                {
-                    const float x = __fmul_rn (sm.ring[(int) ((a0 + w0 + j) & (N - 1))], gain);
-                    y = (w0 + j == 0) ? x : __fadd_rn (__fmul_rn (p.iir_c1, x), __fmul_rn (p.iir_c2, y));
-                }
+                const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
+                xs[4 * q] = __fmul_rn (x4.x, gain); xs[4 * q + 1] = __fmul_rn (x4.y, gain);
+                xs[4 * q + 2] = __fmul_rn (x4.z, gain); xs[4 * q + 3] = __fmul_rn (x4.w, gain);
             }
+            float y = 0.0f;
+            // warm-up over the previous thread's samples (lane 0 of a warp fetches them itself)
+            const int rp = (int) ((a0 + n0 - 16) & (N - 1));
+            #pragma unroll
+            for (int j = 0; j < 16; ++j)
+            {
+                float x = __shfl_up_sync (0xffffffffu, xs[j], 1);
+                if (lane == 0) x = __fmul_rn (sm.ring[rp + j], gain);
+                y = (n0 - 16 + j == 0) ? x : __fadd_rn (__fmul_rn (p.iir_c1, x), __fmul_rn (p.iir_c2, y));
+            }
+            if (t == 0) y = 0.0f;
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
                 const int n = n0 + j;
-                const float x = __fmul_rn (sm.ring[(int) ((a0 + n) & (N - 1))], gain);
-                y = (n == 0) ? x : __fadd_rn (__fmul_rn (p.iir_c1, x), __fmul_rn (p.iir_c2, y));
+                y = (n == 0) ? xs[j] : __fadd_rn (__fmul_rn (p.iir_c1, xs[j]), __fmul_rn (p.iir_c2, y));
                 const float w = (n < M) ? (float) n * (2.0f / N) : 1.0f - (float) (n - M) * (2.0f / N);
                 workf[17 * t + j] = __fmul_rn (y, w);                                             // phys (16 t + j)
             }
         }
-        __syncthreads();                                                                          // (9) ring is free: prefetch the next hop
+        __syncthreads();                                            // ring is free: prefetch the next hop
         if (f + 1 < f_end)
         {
             const long jn = j_new + 1;
@@ -548,61 +571,69 @@ k_analyse (const AnalyseParams p)
             }
             else
             {
-                for (int i = t; i < H; i += T) dst[i] = g[i];       // visible after the barriers below
+                _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = g[i];       // visible after the barriers below
                 if (t == 0) mbar_arrive (&sm.mbar);
             }
         }
+        // spectral record (flat_prod and the pass-3 partials were published by the barrier above)
+        if (t == 0)
+        {
+            double evar = 0.0;
+            #pragma unroll
+            for (int w = 0; w < NW; ++w) evar += sm.red[1][0][w];
+            double product; float flat_state;
+            if (ev == 0xffffffffu) { product = ldexp_normal (total.m, total.e); flat_state = 0.0f; }
+            else { product = sm.flat_prod; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
+            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->flux = flux; rec->lhr = lhr;
+            rec->flat_sum = flat_sum; rec->count = count; rec->product = product; rec->var = var; rec->sie = sie;
+            rec->mean_e = mean_e; rec->evar = evar; rec->max_e = max_e;
+            rec->centroid = centroid; rec->flat_margin = flat_margin; rec->flat_state = silent ? 3.0f : flat_state;
+            rec->have_prev = have_prev ? 1.0f : 0.0f;
+        }
+        if (! silent)
+        {
+            if (! have_prev) { have_prev = true; first_nonsilent = f; }
+            cur ^= 1;                                                                             // :138 prev <- current
+        }
 
-        // =========================== FFT2 (filtered, windowed) chained into FFT3 (inverse) =============
+        // =========================== FFT2 (filtered, windowed) chained into FFT3 =======================
         #pragma unroll
         for (int q = 0; q < Q1; ++q)
             #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1)
-                v[q * R1 + n1] = make_float2 (workf[phys (n1 * 256 + t + T * q)], 0.0f);
-        __syncthreads();                                                                          // (10)
-        fft_stage1_store<R1, false> (v, t, sm.ex, sm.tw1);
-        __syncthreads();                                                                          // (11)
-        fft_stage2<R1, false> (t, sm.ex, sm.tw2);
-        __syncthreads();                                                                          // (12)
+                io.v[q * R1 + n1] = make_float2 (workf[phys (n1 * 256 + t + T * q)], 0.0f);
+        __syncthreads();
+        io = fft_core<R1> (io, t);
         {
-            float2 c3[16];
-            fft_stage3<R1, false> (t, sm.ex, c3);
             // PitchAnalyser::getComplexConjugateMultiplication (PitchAnalyser.h:97-104): Re^2, imaginary cleared
+            V16 c3 = io;
             #pragma unroll
-            for (int s = 0; s < 16; ++s) c3[s] = make_float2 (__fmul_rn (c3[s].x, c3[s].x), 0.0f);
-            chain_permute<R1> (c3, v);
+            for (int s = 0; s < 16; ++s) c3.v[s] = make_float2 (__fmul_rn (c3.v[s].x, c3.v[s].x), 0.0f);
+            chain_permute<R1> (c3.v, io.v);
         }
-        __syncthreads();                                                                          // (13)
-        fft_stage1_store<R1, true> (v, klow<R1> (t), sm.ex, sm.tw1);
-        __syncthreads();                                                                          // (14)
-        fft_stage2<R1, true> (t, sm.ex, sm.tw2);
-        __syncthreads();                                                                          // (15)
-        fft_stage3<R1, true> (t, sm.ex, v);
-        __syncthreads();                                                                          // (16)
+        __syncthreads();
+        io = fft_core<R1> (io, klow<R1> (t));
+        __syncthreads();
         {
             // performRealOnlyInverseTransform scales by 1/N; only the real half d[0..N) can reach the lag search
             const int kl = klow<R1> (t);
             #pragma unroll
-            for (int s = 0; s < 16; ++s) workf[phys (kl + T * out_index<16> (s))] = __fmul_rn (v[s].x, 1.0f / N);
+            for (int s = 0; s < 16; ++s) workf[phys (kl + T * out_index<16> (s))] = __fmul_rn (io.v[s].x, 1.0f / N);
         }
-        __syncthreads();                                                                          // (17)
+        __syncthreads();
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
-        float ac[16];
-        double lsum[16];
         double seg_exc;
         {
             double run = 0.0;
-            #pragma unroll
+            #pragma unroll 4
             for (int j = 0; j < 16; ++j)
             {
                 const int s = 16 * t + j;
                 const float d = workf[17 * t + j];
-                ac[j] = __fmul_rn (__fmul_rn (d, d), (float) s);                                 // PitchAnalyser.h:122-123
-                if (s >= 1) run += (double) ac[j];
-                lsum[j] = run;
+                const float a = __fmul_rn (__fmul_rn (d, d), (float) s);                         // PitchAnalyser.h:122-123
+                if (s >= 1) run += (double) a;
             }
-            // block scan of the segment totals
             double inc = run;
             #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
@@ -613,48 +644,55 @@ k_analyse (const AnalyseParams p)
             seg_exc = __shfl_up_sync (0xffffffffu, inc, 1);
             if (lane == 0) seg_exc = 0.0;
             if (lane == 31) sm.pscan[warp] = inc;
+            if (t == 0) sm.d0 = workf[0];
         }
-        __syncthreads();                                                                          // (18)
+        __syncthreads();
         unsigned first_cross = 0xffffffffu;
         {
-            double base = seg_exc;
+            double run = seg_exc;
             #pragma unroll
-            for (int w = 0; w < NW; ++w) if (w < warp) base += sm.pscan[w];
+            for (int w = 0; w < NW; ++w) if (w < warp) run += sm.pscan[w];
+            const float e_abs = 1.0e-6f * fabsf (sm.d0);
             unsigned long long key = ((unsigned long long) __float_as_uint (100.0f) << 32) | 0xffffffffull;
-            #pragma unroll
+            #pragma unroll 4
             for (int j = 0; j < 16; ++j)
             {
                 const int s = 16 * t + j;
-                const float sumf = (float) (base + lsum[j]);                                     // :145 (fp32 running sum in the reference)
-                float c = (sumf != 0.0f) ? __fdiv_rn (ac[j], sumf) : 0.0f;                       // :146-154
+                const float d = workf[17 * t + j];
+                const float a = __fmul_rn (__fmul_rn (d, d), (float) s);
+                if (s >= 1) run += (double) a;
+                const float sumf = (float) run;                                                  // :145 (fp32 running sum in the reference)
+                float c = (sumf != 0.0f) ? __fdiv_rn (a, sumf) : 0.0f;                           // :146-154
                 if (s == 0) c = 1.0f;                                                             // :141
+                const float u = (sumf != 0.0f) ? __fdividef ((2.0f * fabsf (d) * e_abs + e_abs * e_abs) * (float) s, sumf) : 0.0f;
                 workf[17 * t + j] = c;
+                workg[17 * t + j] = u;
                 if (s >= 2)
                 {
                     if (c < 0.01f && first_cross == 0xffffffffu) first_cross = (unsigned) s;      // :176
                     const unsigned long long k2 = ((unsigned long long) __float_as_uint (c) << 32) | (unsigned) s;
                     if (k2 < key && c >= 0.0f) key = k2;                                          // :171-175 first strict minimum
                 }
-                ac[j] = c;
             }
             const unsigned wfc = warp_minu (first_cross);
             const unsigned long long wkey = warp_minull (key);
             if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
         }
         // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69)
+        float ar[8];
         {
             const float4 a0v = *reinterpret_cast<const float4*> (&sm.specA[b0]);
             const float4 a1v = *reinterpret_cast<const float4*> (&sm.specA[b0 + 4]);
-            const float ar[8] = { a0v.x, a0v.y, a0v.z, a0v.w, a1v.x, a1v.y, a1v.z, a1v.w };
+            ar[0] = a0v.x; ar[1] = a0v.y; ar[2] = a0v.z; ar[3] = a0v.w; ar[4] = a1v.x; ar[5] = a1v.y; ar[6] = a1v.z; ar[7] = a1v.w;
             double hsum = 0.0, hmax = 0.0;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { const double re = (double) ar[j]; mag[j] = re * re; hsum += mag[j]; hmax = fmax (hmax, mag[j]); }
+            for (int j = 0; j < 8; ++j) { const double re = (double) ar[j]; const double mg = re * re; hsum += mg; hmax = fmax (hmax, mg); }
             double s1[1] = { hsum };
             warp_sum<1> (s1);
             const double wm = warp_max (hmax);
             if (lane == 0) { sm.red[0][4][warp] = s1[0]; sm.red[0][5][warp] = wm; }
         }
-        __syncthreads();                                                                          // (19)
+        __syncthreads();
         unsigned s0 = 0xffffffffu;
         unsigned long long gkey = ~0ull;
         double hsum = 0.0, hmax = 0.0;
@@ -673,25 +711,26 @@ k_analyse (const AnalyseParams p)
             float pm = 1.0f;
             float second = 100.0f;
             const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
-            #pragma unroll
+            #pragma unroll 4
             for (int j = 0; j < 16; ++j)
             {
                 const unsigned s = (unsigned) (16 * t + j);
                 if (s < 2u) continue;
+                const float c = workf[17 * t + j];
                 if (crossed)
                 {
-                    if (s <= s0) pm = fminf (pm, relmargin (ac[j], 0.01));
+                    if (s <= s0) pm = fminf (pm, noisy_margin (c, workg[17 * t + j], 0.01f, 0.0f));
                     if (s >= s0 && send == 0xffffffffu)
                     {
                         const bool has_next = (s + 1u < (unsigned) N);
                         const float nxt = has_next ? workf[phys ((int) s + 1)] : 0.0f;
-                        if (! (has_next && nxt < ac[j])) send = s;
+                        if (! (has_next && nxt < c)) send = s;
                     }
                 }
                 else
                 {
-                    pm = fminf (pm, relmargin (ac[j], 0.01));
-                    if (s != gidx) second = fminf (second, ac[j]);
+                    pm = fminf (pm, noisy_margin (c, workg[17 * t + j], 0.01f, 0.0f));
+                    if (s != gidx) second = fminf (second, c);
                 }
             }
             const unsigned wsend = warp_minu (send);
@@ -699,7 +738,7 @@ k_analyse (const AnalyseParams p)
             const float wsec = warp_minf (second);
             if (lane == 0) { sm.ucodes[0][warp] = wsend; sm.fmins[0][warp] = wpm; sm.fmins[1][warp] = wsec; }
         }
-        __syncthreads();                                                                          // (20)
+        __syncthreads();
         if (t == 0)
         {
             unsigned send = 0xffffffffu; float pm = 1.0f, second = 100.0f;
@@ -713,76 +752,89 @@ k_analyse (const AnalyseParams p)
                 const int right = s_end + 1;
                 const float c_end = workf[phys (s_end)];
                 const float c_right = (right < N) ? workf[phys (right)] : 0.0f;      // cnd[N] = Im part of lag 0 = 0
-                for (int s = (int) s0; s < s_end; ++s) pm = fminf (pm, relmargin (workf[phys (s + 1)], workf[phys (s)]));
-                pm = fminf (pm, relmargin (c_end, c_right));
+                #pragma unroll 1
+                for (int s = (int) s0; s < s_end; ++s)
+                    pm = fminf (pm, noisy_margin (workf[phys (s + 1)], workg[phys (s + 1)], workf[phys (s)], workg[phys (s)]));
+                if (right < N) pm = fminf (pm, noisy_margin (c_end, workg[phys (s_end)], c_right, workg[phys (right)]));
                 lag = (c_end <= c_right) ? (float) s_end : (float) right;
             }
             else
             {
                 const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
                 lag = (gidx == 0xffffffffu) ? -1.0f : (float) gidx;                               // :165,188
-                pm = fminf (pm, relmargin (__uint_as_float ((unsigned) (gkey >> 32)), second));
+                pm = fminf (pm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
             }
-            const double f0 = (nyquist * 2.0) / (double) lag;                                     // :57
-            sm.f0 = f0;
-            out[FX_F0] = (float) (f0 / 5000.0);                                                   // RealTimeAnalyser.h:165-166
-            if (dg) { dg[FX_DIAG_LAG] = lag; dg[FX_DIAG_PITCH_MARGIN] = pm; }
+            sm.f0 = (nyquist * 2.0) / (double) lag;                                               // :57
+            rec->lag = lag; rec->pitch_margin = pm;
         }
-        __syncthreads();                                                                          // (21)
+        __syncthreads();
 
         // =========================== harmonic features (HarmonicCharacteristics.h:46-106) =============
         const double f0 = sm.f0;
         const bool hsilent = hsum < 0.005;                                                        // :88
-        const double mean_mag = hsum / (double) M;                                                // :86
+        const double mean_mag = hsum * inv_m;                                                     // :86
         const int f0_bin = (int) floor (f0 / frpb);                                               // :246-249
         {
-            double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0;
-            float pkm = 1.0f;
+            double sum_normed = 0.0, inharm = 0.0;
+            unsigned pgap = 0xffffffffu, peak_mask = 0u;
+            const double inv_hmax = 1.0 / hmax, inv_hsum = 1.0 / hsum;
+            const float mean_f = (float) mean_mag;
             // neighbours bin-2, bin-1, bin+1 (:136-143, loop end exclusive)
-            const double l2 = (b0 >= 2) ? (double) sm.specA[b0 - 2] * (double) sm.specA[b0 - 2] : 0.0;
-            const double l1 = (b0 >= 1) ? (double) sm.specA[b0 - 1] * (double) sm.specA[b0 - 1] : 0.0;
-            const double r1 = (b0 + 8 < M) ? (double) sm.specA[b0 + 8] * (double) sm.specA[b0 + 8] : 0.0;
+            double mgs[11];
+            mgs[0] = (b0 >= 2) ? (double) sm.specA[b0 - 2] * (double) sm.specA[b0 - 2] : 0.0;
+            mgs[1] = (b0 >= 1) ? (double) sm.specA[b0 - 1] * (double) sm.specA[b0 - 1] : 0.0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) mgs[2 + j] = (double) ar[j] * (double) ar[j];
+            mgs[10] = (b0 + 8 < M) ? (double) sm.specA[b0 + 8] * (double) sm.specA[b0 + 8] : 0.0;
             float nm[8];
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
                 const int bin = b0 + j;
-                const double e = mag[j] / hmax;                                                   // :75
+                const double mg = mgs[2 + j];
+                const float mgf = (float) mg;
+                const double e = mg * inv_hmax;                                                   // :75
                 nm[j] = (float) e;
                 sum_normed += e;
-                const double mg = mag[j];
-                pkm = fminf (pkm, relmargin (mg, mean_mag));
+                pgap = min (pgap, ulp_gap (mgf, mean_f));
                 if (mg > mean_mag)
                 {
-                    const double m2 = (j >= 2) ? mag[j - 2] : (j == 1 ? l1 : l2);
-                    const double m1 = (j >= 1) ? mag[j - 1] : l1;
-                    const double p1 = (j < 7) ? mag[j + 1] : r1;
                     // edge clamps (:136-137): the neighbour window is [max (bin-2, 0), min (bin+2, M-1))
-                    bool peak = true;
                     const int lo = bin - 2 > 0 ? bin - 2 : 0;
                     const int hi = bin + 2 < M - 1 ? bin + 2 : M - 1;                             // exclusive
-                    if (bin - 2 >= lo && bin - 2 < hi) { pkm = fminf (pkm, relmargin (m2, mg)); if (m2 > mg) peak = false; }
-                    if (peak && bin - 1 >= lo && bin - 1 < hi) { pkm = fminf (pkm, relmargin (m1, mg)); if (m1 > mg) peak = false; }
-                    if (peak && bin + 1 < hi) { pkm = fminf (pkm, relmargin (p1, mg)); if (p1 > mg) peak = false; }
-                    if (peak)
+                    bool peak = true;
+                    if (bin - 2 >= lo && bin - 2 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j], mgf)); if (mgs[j] > mg) peak = false; }
+                    if (peak && bin - 1 >= lo && bin - 1 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j + 1], mgf)); if (mgs[j + 1] > mg) peak = false; }
+                    if (peak && bin + 1 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j + 3], mgf)); if (mgs[j + 3] > mg) peak = false; }
+                    if (peak) peak_mask |= 1u << j;
+                }
+            }
+            const double npeaks = (double) __popc (peak_mask);
+            // calculateInharmonicity (:212-244) over this thread's peaks
+            if (f0 > 0.0)                                                                         // :98
+            {
+                #pragma unroll 1
+                while (peak_mask)
+                {
+                    const int j = __ffs ((int) peak_mask) - 1;
+                    peak_mask &= peak_mask - 1u;
+                    const int bin = b0 + j;
+                    if (bin == f0_bin) continue;                                                  // :220
+                    const double re = (double) sm.specA[bin];
+                    const double mg = re * re;
+                    double start_f = (double) bin * frpb;                                         // :223
+                    if (start_f == 0.0) start_f = frpb * 0.5;
+                    const double end_f = (double) (bin + 1) * frpb;
+                    const double ra = (start_f == f0) ? 1.0 : fmax (start_f, f0) / fmin (start_f, f0);   // :251-259
+                    const double rb = (end_f == f0) ? 1.0 : fmax (end_f, f0) / fmin (end_f, f0);
+                    if (floor (ra) == floor (rb))                                                 // :232
                     {
-                        npeaks += 1.0;
-                        if (f0 > 0.0 && bin != f0_bin)                                            // :98, :220
-                        {
-                            double start_f = (double) bin * frpb;                                 // :223
-                            if (start_f == 0.0) start_f = frpb * 0.5;
-                            const double end_f = (double) (bin + 1) * frpb;
-                            const double ra = (start_f == f0) ? 1.0 : (start_f > f0 ? start_f / f0 : f0 / start_f);    // :251-259
-                            const double rb = (end_f == f0) ? 1.0 : (end_f > f0 ? end_f / f0 : f0 / end_f);
-                            if (floor (ra) == floor (rb))                                         // :232
-                            {
-                                const double ratio = ra < rb ? ra : rb;
-                                inharm += (ratio - floor (ratio)) * (mg / hsum);                  // :235-239
-                            }
-                        }
+                        const double ratio = ra < rb ? ra : rb;
+                        inharm += (ratio - floor (ratio)) * (mg * inv_hsum);                      // :235-239
                     }
                 }
             }
+            const float pkm = ulps_to_margin (pgap);
             *reinterpret_cast<float4*> (&workf[b0])     = make_float4 (nm[0], nm[1], nm[2], nm[3]);
             *reinterpret_cast<float4*> (&workf[b0 + 4]) = make_float4 (nm[4], nm[5], nm[6], nm[7]);
             double s3[3] = { sum_normed, inharm, npeaks };
@@ -790,7 +842,7 @@ k_analyse (const AnalyseParams p)
             const float wpk = warp_minf (pkm);
             if (lane == 0) { sm.red[1][1][warp] = s3[0]; sm.red[1][2][warp] = s3[1]; sm.red[1][3][warp] = s3[2]; sm.fmins[0][warp] = wpk; }
         }
-        __syncthreads();                                                                          // (22)
+        __syncthreads();
         if (warp == 0)
         {
             // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94)
@@ -815,15 +867,16 @@ k_analyse (const AnalyseParams p)
                 double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f;
                 #pragma unroll
                 for (int w = 0; w < NW; ++w) { sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += sm.red[1][3][w]; pkm = fminf (pkm, sm.fmins[0][w]); }
-                float o_her = 0.0f, o_oer = 0.0f, o_inh = 0.0f;
+                double score = 0.0, even = 0.0, odd = 0.0;
                 if (! hsilent)
                 {
-                    double score = 0.0, even = 0.0, odd = 0.0;
+                    #pragma unroll 1
                     for (int l = 0; l < 15; ++l)
                     {
                         if (sm.her_bins[l] == f0_bin) continue;                                   // :163-164
                         score += (double) sm.her_terms[l];
                     }
+                    #pragma unroll 1
                     for (int h = 1; h <= 3; ++h)
                     {
                         if (sm.her_bins[14 + h] >= M) break;                                      // :174-175
@@ -831,29 +884,13 @@ k_analyse (const AnalyseParams p)
                         if (h % 2 == 0) even += bm; else odd += bm;
                         score += bm;
                     }
-                    double her = score / sum_normed;
-                    her = her > 1.0 ? 1.0 : her; her = her < 0.0 ? 0.0 : her;
-                    double oer = 1.0;
-                    if (odd > 0.0) oer = even / odd;
-                    oer = oer > 1.0 ? 1.0 : oer; oer = oer < 0.0 ? 0.0 : oer;
-                    o_her = (float) log10 ((double) (float) her * 9.0 + 1.0);                     // :101-103
-                    o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);
-                    o_inh = (float) log10 (inharm * 9.0 + 1.0);
                 }
-                else { npeaks = 0.0; }
-                out[FX_HER] = o_her;
-                out[FX_OER] = o_her;                                                              // RealTimeAnalyser.h:171 stores HER in the OER slot
-                out[FX_INHARM] = o_inh;
-                if (dg)
-                {
-                    dg[FX_DIAG_TRUE_OER] = o_oer;
-                    dg[FX_DIAG_NUM_PEAKS] = (float) npeaks;
-                    dg[FX_DIAG_PEAK_MARGIN] = pkm;
-                    dg[FX_DIAG_GATE_MARGIN] = fminf (dg[FX_DIAG_GATE_MARGIN], relmargin (hsum, 0.005));
-                }
+                rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
+                rec->score = score; rec->even = even; rec->odd = odd;
+                rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
             }
         }
-        __syncthreads();                                                                          // (23) work array and reduction slots are reused by the next frame
+        __syncthreads();                                            // work array and reduction slots are reused by the next frame
     }
 
     // ---- chunk epilogue ----------------------------------------------------------------------------------
@@ -869,6 +906,85 @@ k_analyse (const AnalyseParams p)
         const long a_end = (p.first_hop + f_end) * (long) H;
         float* to = p.tail_out + track * (long) (N - H);
         for (int i = t; i < N - H; i += T) to[i] = sm.ring[(int) ((a_end - (N - H) + i) & (N - 1))];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1b: the scalar tail of both analyser bodies, one thread per frame.
+__global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
+{
+    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n_rows) return;
+    const FrameRec r = p.rec[idx];
+    float* out = p.raw + idx * FX_NUM_FEATURES;
+    const int N = p.window, M = N / 2;
+    const double nyquist = p.sample_rate / 2.0;
+
+    // ---- spectral body (SpectralCharacteristics.h:100-143, :145-200) ------------------------------------------
+    const float rms = (float) sqrt (r.rms_sum / (double) N);                                      // getRMSLevel
+    const float log_rms = (float) log10 ((double) __fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));       // RealTimeAnalyser.h:208
+    const double eps = 0.01 * (double) log_rms;                                                   // :108
+    const bool silent = ! (r.mag_sum > 0.05);                                                     // :121-123
+    float gate_margin = fminf (relmargin_d (r.mag_sum, 0.05), relmargin_d (r.max_e, 0.0001));
+    float o_centroid = 0.0f, o_spread = 0.0f, o_flat = 0.0f, o_ler = 0.0f, o_flux = 0.0f, o_slope = 0.0f;
+    if (! silent)
+    {
+        const float max_flux = (float) (M * (M + 1)) / 2.0f;                                      // :111
+        const double inv = 1.0 / (r.count > 0.0 ? r.count : 1.0);                                 // :130
+        const float flat = r.flat_sum > eps ? (float) (pow (r.product, inv) / (inv * r.flat_sum)) : 0.0f;     // :57-60
+        o_flat = (float) log10 ((double) flat * 9.0 + 1.0);                                       // :132
+        const float c = __fdiv_rn (r.centroid, (float) (nyquist / 2.0));                          // :133
+        o_centroid = (float) log10 ((double) __fadd_rn (__fmul_rn (c, 9.0f), 1.0f));              // :134
+        const float max_spread = (float) (((double) r.centroid / nyquist) * (1.0 - ((double) r.centroid / nyquist)));   // :140
+        o_spread = (float) ((r.var / r.mag_sum) / (double) max_spread);                           // :141
+        o_ler = (float) (r.lhr / r.mag_sum);                                                      // :125
+        o_flux = r.have_prev != 0.0f ? (float) (r.flux / (double) max_flux) : 0.0f;               // :112 (K2 fixes the chunk's first non-silent frame)
+    }
+    if (r.max_e > 0.0001)                                                                         // :165-167
+    {
+        const double energy_var = r.evar / (double) M;
+        const double bin_std = sqrt (p.bin_var), energy_std = sqrt (energy_var);
+        const double rr = (r.sie - ((double) M * r.mean_e * 0.5)) / (double) ((float) M - 1.0f) * energy_std * bin_std;   // :195
+        o_slope = (float) (rr * (bin_std / energy_std));                                          // :198
+    }
+
+    // ---- harmonic body (PitchAnalyser.h:57, RealTimeAnalyser.h:165-172, HarmonicCharacteristics.h:88-105) ---------
+    const double f0 = (nyquist * 2.0) / (double) r.lag;
+    float o_her = 0.0f, o_oer = 0.0f, o_inh = 0.0f;
+    if (! (r.hsum < 0.005))
+    {
+        double her = r.score / r.sum_normed;                                                      // :186-188
+        her = her > 1.0 ? 1.0 : her; her = her < 0.0 ? 0.0 : her;
+        double oer = 1.0;
+        if (r.odd > 0.0) oer = r.even / r.odd;                                                    // :190-195
+        oer = oer > 1.0 ? 1.0 : oer; oer = oer < 0.0 ? 0.0 : oer;
+        o_her = (float) log10 ((double) (float) her * 9.0 + 1.0);                                 // :101-103
+        o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);
+        o_inh = (float) log10 (r.inharm * 9.0 + 1.0);
+    }
+    gate_margin = fminf (gate_margin, relmargin_d (r.hsum, 0.005));
+
+    out[FX_ONSET] = 0.0f;
+    out[FX_RMS] = log_rms;
+    out[FX_F0] = (float) (f0 / 5000.0);
+    out[FX_CENTROID] = o_centroid; out[FX_SPREAD] = o_spread; out[FX_FLATNESS] = o_flat;
+    out[FX_LER] = o_ler; out[FX_FLUX] = o_flux; out[FX_SLOPE] = o_slope;
+    out[FX_HER] = o_her;
+    out[FX_OER] = o_her;                                                                          // RealTimeAnalyser.h:171 stores HER in the OER slot
+    out[FX_INHARM] = o_inh;
+    if (p.diag)
+    {
+        float* dg = p.diag + idx * FX_NUM_DIAG;
+        dg[FX_DIAG_TRUE_OER] = o_oer;
+        dg[FX_DIAG_LAG] = r.lag;
+        dg[FX_DIAG_PITCH_MARGIN] = r.pitch_margin;
+        dg[FX_DIAG_NUM_PEAKS] = r.npeaks;
+        dg[FX_DIAG_PEAK_MARGIN] = r.peak_margin;
+        dg[FX_DIAG_FLAT_COUNT] = (float) r.count;
+        dg[FX_DIAG_FLAT_MARGIN] = r.flat_margin;
+        dg[FX_DIAG_GATE_MARGIN] = gate_margin;
+        dg[FX_DIAG_ONSET_MARGIN] = 1.0f;
+        dg[FX_DIAG_FLAT_STATE] = r.flat_state;
     }
 }
 
@@ -912,6 +1028,13 @@ cudaError_t launch_analyse (int window, long n_tracks, const AnalyseParams& p, c
         case 4096: return launch_t<16> (n_tracks, p, stream);
         default:   return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_finalize (const FinalizeParams& p, cudaStream_t stream)
+{
+    if (p.n_rows <= 0) return cudaSuccess;
+    k_finalize<<<(unsigned) ((p.n_rows + 127) / 128), 128, 0, stream>>> (p);
+    return cudaGetLastError();
 }
 
 } // namespace fx

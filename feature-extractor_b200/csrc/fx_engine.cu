@@ -64,6 +64,8 @@ struct fx_engine
     // engine-owned result buffers (host API, streaming)
     float *d_raw = nullptr, *d_smooth = nullptr, *d_diag = nullptr;
     long  result_capacity = 0;          // frames per track
+    fx::FrameRec* d_rec = nullptr;      // K1 -> K1b hand-over, [T][rec_capacity]
+    long  rec_capacity = 0;
     float *d_latest = nullptr, *h_latest = nullptr;      // [T][14]
 
     // host API pipeline
@@ -78,6 +80,11 @@ struct fx_engine
     long   rpos = 0;                       // samples consumed per track (all tracks advance together)
     std::vector<fx_group> groups;
     long   stage_hops = 0;
+
+    // optional per-kernel timing (bench.py roofline)
+    bool   profiling = false;
+    struct ProfRec { cudaEvent_t a, b, c; };
+    std::vector<ProfRec> prof_pending, prof_free;
 };
 
 namespace {
@@ -161,6 +168,17 @@ fx_status ensure_results (fx_engine* e, long frames)
     return FX_OK;
 }
 
+fx_status ensure_records (fx_engine* e, long frames)
+{
+    if (frames <= e->rec_capacity) return FX_OK;
+    FX_CUDA (e, cudaDeviceSynchronize());
+    cudaFree (e->d_rec);
+    e->d_rec = nullptr; e->rec_capacity = 0;
+    FX_CUDA (e, cudaMalloc (&e->d_rec, (size_t) e->cfg.n_tracks * (size_t) frames * sizeof (fx::FrameRec)));
+    e->rec_capacity = frames;
+    return FX_OK;
+}
+
 // how many chunks per track: enough CTAs for a few waves over the machine, but never chunks so short that the
 // window refill at a chunk start dominates
 int choose_chunks (const fx_engine* e, long n_tracks, long frames)
@@ -192,13 +210,26 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
     a.tw1 = e->d_tw1; a.tw2 = e->d_tw2;
-    a.raw = d_raw; a.diag = d_diag;
+    a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
     const size_t coff = (size_t) t0 * (size_t) n_chunks;
     a.first_spec = e->d_first_spec + coff * e->M;
     a.last_spec  = e->d_last_spec + coff * e->M;
     a.first_idx  = e->d_first_idx + coff;
+    fx_engine::ProfRec pr{};
+    if (e->profiling)
+    {
+        if (! e->prof_free.empty()) { pr = e->prof_free.back(); e->prof_free.pop_back(); }
+        else { FX_CUDA (e, cudaEventCreate (&pr.a)); FX_CUDA (e, cudaEventCreate (&pr.b)); FX_CUDA (e, cudaEventCreate (&pr.c)); }
+        FX_CUDA (e, cudaEventRecord (pr.a, s));
+    }
     FX_CUDA (e, launch_analyse (e->N, nt, a, s));
+    if (e->profiling) FX_CUDA (e, cudaEventRecord (pr.b, s));
+
+    FinalizeParams fz{};
+    fz.rec = a.rec; fz.n_rows = (long) nt * frames; fz.window = e->N; fz.sample_rate = e->cfg.sample_rate; fz.bin_var = e->bin_var;
+    fz.raw = d_raw; fz.diag = d_diag;
+    FX_CUDA (e, launch_finalize (fz, s));
 
     FluxFixParams fp{};
     fp.n_frames = (int) frames; fp.n_chunks = n_chunks; fp.m = e->M;
@@ -216,7 +247,8 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     sp.onset_type = e->d_type + t0; sp.onset_hist = e->d_hist + t0; sp.onset_mult = e->d_mult + t0; sp.onset_reset = e->d_reset + t0;
     sp.latest = d_latest;
     FX_CUDA (e, launch_smooth (nt, sp, s));
-    e->launches += 4;
+    if (e->profiling) { FX_CUDA (e, cudaEventRecord (pr.c, s)); e->prof_pending.push_back (pr); }
+    e->launches += 5;
     return FX_OK;
 }
 
@@ -229,11 +261,13 @@ void free_engine (fx_engine* e)
     cudaFree (e->d_gain); cudaFree (e->d_mult); cudaFree (e->d_type); cudaFree (e->d_hist); cudaFree (e->d_reset);
     for (int i = 0; i < 2; ++i) { cudaFree (e->d_tail[i]); cudaFree (e->d_prev[i]); cudaFree (e->d_hrows[i]); }
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
-    cudaFree (e->d_raw); cudaFree (e->d_smooth); cudaFree (e->d_diag); cudaFree (e->d_latest);
+    cudaFree (e->d_raw); cudaFree (e->d_smooth); cudaFree (e->d_diag); cudaFree (e->d_latest); cudaFree (e->d_rec);
     if (e->h_latest) cudaFreeHost (e->h_latest);
     for (int i = 0; i < 3; ++i) { cudaFree (e->d_audio_slot[i]); if (e->pipe_stream[i]) cudaStreamDestroy (e->pipe_stream[i]); }
     if (e->h_ring) cudaFreeHost (e->h_ring);
     for (auto& g : e->groups) { cudaFree (g.d_stage); if (g.stream) cudaStreamDestroy (g.stream); }
+    for (auto* v : { &e->prof_pending, &e->prof_free })
+        for (auto& pr : *v) { cudaEventDestroy (pr.a); cudaEventDestroy (pr.b); cudaEventDestroy (pr.c); }
     if (e->stream) cudaStreamDestroy (e->stream);
     delete e;
 }
@@ -447,6 +481,8 @@ fx_status fx_analyse_device (fx_engine* e, const float* d_audio, long track_stri
     const int n_chunks = choose_chunks (e, T, frames);
     st = ensure_chunks (e, T * n_chunks);
     if (st != FX_OK) return st;
+    st = ensure_records (e, frames);
+    if (st != FX_OK) return st;
     if (! d_raw)
     {
         st = ensure_results (e, frames);
@@ -492,6 +528,8 @@ fx_status fx_analyse_host (fx_engine* e, const float* audio, long track_stride, 
     if (st != FX_OK) return st;
     FX_CUDA (e, cudaStreamSynchronize (e->stream));
     st = ensure_results (e, frames);
+    if (st != FX_OK) return st;
+    st = ensure_records (e, frames);
     if (st != FX_OK) return st;
     const int n_chunks = choose_chunks (e, per, frames);
     st = ensure_chunks (e, T * n_chunks);
@@ -563,6 +601,8 @@ fx_status fx_process (fx_engine* e, long* n_new_frames)
     const long n = hops * H;
 
     fx_status st = ensure_results (e, hops);
+    if (st != FX_OK) return st;
+    st = ensure_records (e, hops);
     if (st != FX_OK) return st;
     // parameter upload and the chunk buffers are shared by the groups: settle them before fanning out
     st = upload_params (e, e->stream);
@@ -646,5 +686,41 @@ fx_status fx_synth_device (fx_engine* e, float* d_audio, long track_stride, long
 }
 
 uint64_t fx_kernel_launches (const fx_engine* e) { return e ? e->launches.load() : 0; }
+
+fx_status fx_profile_enable (fx_engine* e, int on)
+{
+    if (! e) return FX_ERR_INVALID_ARG;
+    e->profiling = on != 0;
+    return FX_OK;
+}
+
+fx_status fx_profile_read (fx_engine* e, double* ms_analyse, double* ms_post, long* n_calls)
+{
+    if (! e) return FX_ERR_INVALID_ARG;
+    FX_CUDA (e, cudaSetDevice (e->cfg.device));
+    double ka = 0.0, kp = 0.0;
+    long n = 0;
+    for (auto& pr : e->prof_pending)
+    {
+        FX_CUDA (e, cudaEventSynchronize (pr.c));
+        float m1 = 0.0f, m2 = 0.0f;
+        FX_CUDA (e, cudaEventElapsedTime (&m1, pr.a, pr.b));
+        FX_CUDA (e, cudaEventElapsedTime (&m2, pr.b, pr.c));
+        ka += m1; kp += m2; ++n;
+        e->prof_free.push_back (pr);
+    }
+    e->prof_pending.clear();
+    if (ms_analyse) *ms_analyse = ka;
+    if (ms_post) *ms_post = kp;
+    if (n_calls) *n_calls = n;
+    return FX_OK;
+}
+
+fx_status fx_measure_fp32_peak (int device, double* tflops)
+{
+    if (! tflops) return FX_ERR_INVALID_ARG;
+    if (cudaSetDevice (device) != cudaSuccess) return FX_ERR_NO_DEVICE;
+    return fx::measure_fp32_peak (tflops) == cudaSuccess ? FX_OK : FX_ERR_CUDA;
+}
 
 } // extern "C"

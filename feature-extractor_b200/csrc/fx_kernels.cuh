@@ -10,6 +10,14 @@ namespace fx {
 constexpr int kHistRows   = 32;   // raw feature rows carried between calls (10-tap smoothing + <=16-deep onset window + 5)
 constexpr int kMaxOnsetHist = 16;
 
+// Per-frame sums K1 leaves for K1b (k_finalize).  fp64 wherever the reference accumulates in double.
+struct FrameRec
+{
+    double rms_sum, mag_sum, weighted, flux, lhr, flat_sum, count, product, var, sie, mean_e, evar, max_e;   // spectral body
+    double hsum, sum_normed, inharm, score, even, odd;                                                       // harmonic body
+    float  centroid, flat_margin, flat_state, have_prev, lag, pitch_margin, npeaks, peak_margin;
+};
+
 // ---- K1: per-(track, chunk) frame walker ------------------------------------------------------------
 struct AnalyseParams
 {
@@ -33,8 +41,7 @@ struct AnalyseParams
     const float2* tw1;             // global twiddle tables (fx_fft.cuh layout)
     const float2* tw2;
     // outputs
-    float*       raw;              // [n_tracks][n_frames][12]
-    float*       diag;             // [n_tracks][n_frames][FX_NUM_DIAG] (may be null)
+    FrameRec*    rec;              // [n_tracks][n_frames]
     float*       first_spec;       // [n_tracks][n_chunks][M]  Re spectrum (windowed path) of the chunk's first non-silent frame
     float*       last_spec;        // [n_tracks][n_chunks][M]  ... of its last non-silent frame
     int*         first_idx;        // [n_tracks][n_chunks]     frame index of the first non-silent frame, -1 if none
@@ -43,6 +50,19 @@ struct AnalyseParams
 cudaError_t launch_analyse (int window, long n_tracks, const AnalyseParams& p, cudaStream_t stream);
 cudaError_t configure_analyse (int window);             // opt in to the dynamic shared memory the kernel needs
 size_t      analyse_smem_bytes (int window);
+
+// ---- K1b: scalar tail (pow / log10 / sqrt, gates, clamps), one thread per frame --------------------
+struct FinalizeParams
+{
+    const FrameRec* rec;
+    long         n_rows;           // n_tracks * n_frames
+    int          window;
+    double       sample_rate;
+    double       bin_var;
+    float*       raw;              // [n_rows][12]
+    float*       diag;             // [n_rows][FX_NUM_DIAG] (may be null)
+};
+cudaError_t launch_finalize (const FinalizeParams& p, cudaStream_t stream);
 
 // ---- K2: flux of each chunk's first non-silent frame against the carried previous spectrum ----------
 struct FluxFixParams
@@ -72,12 +92,15 @@ struct SmoothParams
     const int*   onset_hist;
     const float* onset_mult;
     const long*  onset_reset;      // [n_tracks] absolute frame index at which the onset histories were last cleared
-    float*       latest;           // [n_tracks][12 + 1] smoothed vector of the newest frame + frame count (may be null)
+    float*       latest;           // [n_tracks][12 + 2] smoothed vector of the newest frame + 64-bit frame count as two words (may be null)
 };
 cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t stream);
 
 // ---- synthetic workload ------------------------------------------------------------------------------
 cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
                           double sample_rate, uint64_t seed, cudaStream_t stream);
+
+// ---- FP32 FMA microbenchmark ---------------------------------------------------------------------------
+cudaError_t measure_fp32_peak (double* tflops);
 
 } // namespace fx

@@ -278,4 +278,56 @@ cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, lon
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 8 independent FMA chains per thread, 2 flops per FMA; enough CTAs to fill every SM several times over
+__global__ void __launch_bounds__ (256) k_fma_peak (float* sink, int iters, float a, float b)
+{
+    float r0 = threadIdx.x * 1e-3f, r1 = r0 + 1.0f, r2 = r0 + 2.0f, r3 = r0 + 3.0f, r4 = r0 + 4.0f, r5 = r0 + 5.0f, r6 = r0 + 6.0f, r7 = r0 + 7.0f;
+    for (int i = 0; i < iters; ++i)
+    {
+        #pragma unroll
+        for (int u = 0; u < 16; ++u)
+        {
+            r0 = fmaf (r0, a, b); r1 = fmaf (r1, a, b); r2 = fmaf (r2, a, b); r3 = fmaf (r3, a, b);
+            r4 = fmaf (r4, a, b); r5 = fmaf (r5, a, b); r6 = fmaf (r6, a, b); r7 = fmaf (r7, a, b);
+        }
+    }
+    const float s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 123.456f) sink[0] = s;
+}
+
+cudaError_t measure_fp32_peak (double* tflops)
+{
+    cudaDeviceProp prop{};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice (&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaGetDeviceProperties (&prop, dev);
+    if (e != cudaSuccess) return e;
+    float* sink = nullptr;
+    e = cudaMalloc (&sink, 64);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate (&a); cudaEventCreate (&b);
+    const int blocks = prop.multiProcessorCount * 16, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep)
+    {
+        cudaEventRecord (a);
+        k_fma_peak<<<blocks, 256>>> (sink, iters, 0.999f, 1e-4f);
+        cudaEventRecord (b);
+        e = cudaEventSynchronize (b);
+        if (e != cudaSuccess) break;
+        float ms = 0.0f;
+        cudaEventElapsedTime (&ms, a, b);
+        const double flops = (double) blocks * 256.0 * (double) iters * 16.0 * 8.0 * 2.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy (a); cudaEventDestroy (b);
+    cudaFree (sink);
+    *tflops = best;
+    return e;
+}
+
 } // namespace fx

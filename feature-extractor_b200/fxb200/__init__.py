@@ -29,6 +29,7 @@ EXPORTS = (
     "fx_default_config", "fx_engine_create", "fx_engine_destroy", "fx_last_error", "fx_version", "fx_set_gain",
     "fx_set_onset", "fx_reset", "fx_analyse_host", "fx_analyse_device", "fx_push_block", "fx_process",
     "fx_poll_features", "fx_flush", "fx_osc_order", "fx_synth_device", "fx_kernel_launches",
+    "fx_profile_enable", "fx_profile_read", "fx_measure_fp32_peak",
 )
 
 
@@ -91,6 +92,12 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.fx_synth_device.restype = c_int
     lib.fx_kernel_launches.argtypes = [c_void_p]
     lib.fx_kernel_launches.restype = c_uint64
+    lib.fx_profile_enable.argtypes = [c_void_p, c_int]
+    lib.fx_profile_enable.restype = c_int
+    lib.fx_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_long)]
+    lib.fx_profile_read.restype = c_int
+    lib.fx_measure_fp32_peak.argtypes = [c_int, POINTER(c_double)]
+    lib.fx_measure_fp32_peak.restype = c_int
     if path is None:
         _lib = lib
     return lib
@@ -212,9 +219,27 @@ class Engine:
     def flush(self):
         self._check(self.lib.fx_flush(self._h), "fx_flush")
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.fx_profile_enable(self._h, 1 if on else 0), "fx_profile_enable")
+
+    def profile_read(self):
+        """(ms in k_analyse, ms in the post kernels, bracketed calls) since the last read"""
+        a, b, n = c_double(0), c_double(0), c_long(0)
+        self._check(self.lib.fx_profile_read(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)), "fx_profile_read")
+        return a.value, b.value, n.value
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.fx_kernel_launches(self._h))
+
+
+def measure_fp32_peak(device: int = 0) -> float:
+    lib = load_library()
+    tf = c_double(0)
+    st = lib.fx_measure_fp32_peak(device, ctypes.byref(tf))
+    if st != 0:
+        raise FxError(f"fx_measure_fp32_peak failed ({st})")
+    return tf.value
 
 
 def osc_order(vec12: np.ndarray, n_out: int = 12) -> np.ndarray:

@@ -141,6 +141,13 @@ fx_status   fx_synth_device (fx_engine* e, float* d_audio, long track_stride, lo
                              long first_track, uint64_t seed, void* stream);
 /* number of kernels this engine has launched since creation */
 uint64_t    fx_kernel_launches (const fx_engine* e);
+/* Per-kernel device timing: when enabled, every call brackets the analysis kernel (k_analyse) and the small
+ * post kernels with CUDA events on the stream they are launched on.  fx_profile_read synchronises those events
+ * and returns the accumulated milliseconds and the number of bracketed calls since the last read. */
+fx_status   fx_profile_enable (fx_engine* e, int on);
+fx_status   fx_profile_read   (fx_engine* e, double* ms_analyse, double* ms_post, long* n_calls);
+/* FP32 FMA microbenchmark (registers only) for the compute roofline denominator: achieved TFLOP/s on `device`. */
+fx_status   fx_measure_fp32_peak (int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -409,13 +409,26 @@ static int detect_onset (track* t)
     }
 }
 
-/* PitchAnalyser::estimatePitch -- PitchAnalyser.h:24-59, :83-217.  Returns f0 (Hz), sets lag + margin. */
+/* Margin of a comparison between two cnd values whose fp32 uncertainties are ua, ub: the part of the relative
+ * gap that exceeds the uncertainty.  0 means "decided by rounding noise". */
+static float noisy_margin (float a, float ua, float b, float ub)
+{
+    const float gap = fabsf (a - b) - (ua + ub);
+    const float m = fabsf (a) > fabsf (b) ? fabsf (a) : fabsf (b);
+    if (! (gap > 0.0f) || ! (m > 0.0f)) return 0.0f;
+    return gap / m;
+}
+
+/* PitchAnalyser::estimatePitch -- PitchAnalyser.h:24-59, :83-217.  Returns f0 (Hz), sets lag + margin.
+ * The margin (diagnostic only) discounts the fp32 noise floor of the autocorrelation: d[s] carries an absolute
+ * error of about 1e-6 d[0] after two fp32 FFTs, so cnd[s] = d[s]^2 s / sum carries u[s] = (2 |d[s]| e + e^2) s / sum. */
 static double estimate_pitch (track* t, const float* freq, double nyquist)
 {
     const int N = t->n, two_n = 2 * t->n;
     int s, lag = -1;
     float sum = 0.0f, global_min = 100.0f, global_min_index = -1.0f, second_min = 100.0f, lag_estimate;
-    float margin = 1.0f;
+    float margin = 1.0f, e_abs;
+    float* unc = (float*) t->scratch;          /* N floats of scratch: uncertainty of cnd[s] */
     int crossed = 0;
 
     /* getComplexConjugateMultiplication (:83-108): Re^2, imaginary cleared */
@@ -426,6 +439,8 @@ static double estimate_pitch (track* t, const float* freq, double nyquist)
     }
     /* getAutoCorrelationFromConjugateMultiplication (:110-127) */
     fft_real_inverse (&t->inv, t->ac, t->scratch);
+    e_abs = 1.0e-6f * fabsf (t->ac[0]);
+    for (s = 0; s < N; ++s) unc[s] = fabsf (t->ac[s]);       /* |d[s]| for now */
     for (s = 0; s < two_n; ++s) t->ac[s] = t->ac[s] * t->ac[s] * s;
     /* getCumulativeNormalisedDifferenceFromAutoCorrelationBuffer (:129-159): sequential fp32 sum */
     t->cnd[0] = 1.0f;
@@ -433,23 +448,23 @@ static double estimate_pitch (track* t, const float* freq, double nyquist)
         const float value = t->ac[s];
         sum += value;
         t->cnd[s] = (sum != 0.0f) ? value / sum : 0.0f;
+        if (s < N) unc[s] = (sum != 0.0f) ? (2.0f * unc[s] * e_abs + e_abs * e_abs) * (float) s / sum : 0.0f;
     }
     /* getLagEstimateFromCumulativeDifference (:161-190), threshold 0.01 */
     for (s = 2; s < N; ++s) {
         if (t->cnd[s] < global_min) { second_min = global_min; global_min_index = (float) s; global_min = t->cnd[s]; }
         else if (t->cnd[s] < second_min) second_min = t->cnd[s];
-        margin_min (&margin, relmargin (t->cnd[s], 0.01f));
+        margin_min (&margin, noisy_margin (t->cnd[s], unc[s], 0.01f, 0.0f));
         if (t->cnd[s] < 0.01f) {
             int right;
             while (s + 1 < N && t->cnd[s + 1] < t->cnd[s]) {
-                margin_min (&margin, relmargin (t->cnd[s + 1], t->cnd[s]));
+                margin_min (&margin, noisy_margin (t->cnd[s + 1], unc[s + 1], t->cnd[s], unc[s]));
                 s++;
             }
-            if (s + 1 < N) margin_min (&margin, relmargin (t->cnd[s + 1], t->cnd[s]));
+            if (s + 1 < N) margin_min (&margin, noisy_margin (t->cnd[s + 1], unc[s + 1], t->cnd[s], unc[s]));
             /* getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-217): leftNeighbour == lagEstimate
              * always, so the parabolic branch is unreachable and the result is an integer lag */
             right = s + ((s < N + 1) ? 1 : 0);
-            margin_min (&margin, relmargin (t->cnd[s], t->cnd[right]));
             lag = (t->cnd[s] <= t->cnd[right]) ? s : right;
             crossed = 1;
             break;
