@@ -84,6 +84,16 @@ __device__ __forceinline__ float noisy_margin (float a, float ua, float b, float
     return (gap > 0.0f && m > 0.0f) ? __fdividef (gap, m) : 0.0f;
 }
 
+// fp32 uncertainty of cnd[s] = d^2 s / sum when d carries an absolute error e_abs: (2 |d| e + e^2) s / sum = c r (2 + r),
+// r = e / |d|.  d == 0 means the value is pure rounding noise.
+__device__ __forceinline__ float cnd_uncertainty (float c, float d, float e_abs)
+{
+    const float ad = fabsf (d);
+    if (! (ad > 0.0f)) return 1.0e30f;
+    const float r = __fdividef (e_abs, ad);
+    return c * r * (2.0f + r);
+}
+
 // Conservative (never over-estimating) relative gap between two non-negative fp32 values from the distance of
 // their bit patterns: |a - b| / max (a, b) >= ulps * 2^-24.  Three integer instructions per comparison.
 __device__ __forceinline__ unsigned ulp_gap (float a, float b)
@@ -182,8 +192,6 @@ template <int R1> struct Smem
     double   flat_prod;
     double   f0;
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
-    float    her_terms[18];
-    int      her_bins[18];
     uint64_t mbar;
 };
 
@@ -352,6 +360,7 @@ k_analyse (const AnalyseParams p)
         // =========================== spectral features, pass 1 ========================================
         float cr[8];
         ME lprod = me_one();
+        int e_budget = 0;                // sum of |exponent| over this thread's gated bins: bounds how far its running product can move
         {
             const float4 c0 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0]);
             const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0 + 4]);
@@ -362,6 +371,7 @@ k_analyse (const AnalyseParams p)
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
             unsigned fgap = 0xffffffffu;
             const float eps_f = (float) eps;
+            double mprod = 1.0; int esum = 0;
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
@@ -377,13 +387,17 @@ k_analyse (const AnalyseParams p)
                 {
                     flat_sum += mg;
                     count += 1.0;
-                    lprod = me_mul (lprod, me_from (mg));
+                    const ME q = me_from (mg);
+                    mprod *= q.m;                                                                // >= 2^-8: no renormalisation needed
+                    esum += q.e;
+                    e_budget += (q.e < 0 ? -q.e : q.e) + 1;
                 }
                 fgap = min (fgap, ulp_gap ((float) mg, eps_f));
                 const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
                 weighted += fc * mg;
                 maxmag = fmax (maxmag, mg);
             }
+            lprod = me_from (mprod); lprod.e += esum;
             double s6[6] = { mag_sum, weighted, flux, lhr, flat_sum, count };
             warp_sum<6> (s6);
             const double wmax = warp_max (maxmag);
@@ -438,7 +452,6 @@ k_analyse (const AnalyseParams p)
         {
             double var = 0.0, se = 0.0, sie = 0.0;
             const double cn = (double) centroid / nyquist;                                        // :137
-            ME run = prefix;
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
@@ -449,15 +462,29 @@ k_analyse (const AnalyseParams p)
                 const double e = mg * inv_max_e;                                                  // :172
                 se += e;
                 sie += (double) bin * e;                                                          // :175
-                if (mg > eps)
+            }
+            // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is
+            // still in range and the exponent budget of its bins reaches a limit; a prefix already out of range
+            // means an earlier thread owns the first event.
+            if (prefix.e < 1025 && prefix.e > -1022 && (prefix.e + e_budget >= 1025 || prefix.e - e_budget <= -1022))
+            {
+                ME run = prefix;
+                #pragma unroll 1
+                for (int j = 0; j < 8; ++j)
                 {
-                    const ME nxt = me_mul (run, me_from (mg));
-                    if (ev_code == 0xffffffffu && (nxt.e >= 1025 || nxt.e <= -1022))
+                    const double re = (double) sm.specB[cur][b0 + j];
+                    const double mg = re * re;
+                    if (mg > eps)
                     {
-                        ev_code = (unsigned) bin * 2u + (nxt.e >= 1025 ? 1u : 0u);
-                        ev_run = run;
+                        const ME nxt = me_mul (run, me_from (mg));
+                        if (nxt.e >= 1025 || nxt.e <= -1022)
+                        {
+                            ev_code = (unsigned) (b0 + j) * 2u + (nxt.e >= 1025 ? 1u : 0u);
+                            ev_run = run;
+                            break;
+                        }
+                        run = nxt;
                     }
-                    run = nxt;
                 }
             }
             double s3[3] = { var, se, sie };
@@ -496,16 +523,25 @@ k_analyse (const AnalyseParams p)
                 else
                 {
                     prod = ldexp_normal (ev_run.m, ev_run.e);
+                    int b = (int) (ev >> 1);
                     #pragma unroll 1
-                    for (int b = (int) (ev >> 1); b < M; ++b)
+                    for (; (b & 3) != 0; ++b)
                     {
                         const double re = (double) sm.specB[cur][b];
                         const double mg = re * re;
-                        if (mg > eps)
-                        {
-                            prod *= mg;
-                            if (prod == 0.0 || isinf (prod)) break;
-                        }
+                        if (mg > eps) prod *= mg;
+                    }
+                    // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group
+                    #pragma unroll 1
+                    for (; b < M && prod != 0.0 && ! isinf (prod); b += 4)
+                    {
+                        const float4 v4 = *reinterpret_cast<const float4*> (&sm.specB[cur][b]);
+                        const double m0 = (double) v4.x * (double) v4.x, m1 = (double) v4.y * (double) v4.y;
+                        const double m2 = (double) v4.z * (double) v4.z, m3 = (double) v4.w * (double) v4.w;
+                        if (m0 > eps) prod *= m0;
+                        if (m1 > eps) prod *= m1;
+                        if (m2 > eps) prod *= m2;
+                        if (m3 > eps) prod *= m3;
                     }
                 }
                 sm.flat_prod = prod;
@@ -625,16 +661,15 @@ k_analyse (const AnalyseParams p)
         // =========================== pitch: cumulative normalised difference + lag search ==============
         double seg_exc;
         {
-            double run = 0.0;
-            #pragma unroll 4
+            float runf = 0.0f;
+            #pragma unroll 8
             for (int j = 0; j < 16; ++j)
             {
                 const int s = 16 * t + j;
                 const float d = workf[17 * t + j];
-                const float a = __fmul_rn (__fmul_rn (d, d), (float) s);                         // PitchAnalyser.h:122-123
-                if (s >= 1) run += (double) a;
+                runf += __fmul_rn (__fmul_rn (d, d), (float) s);                                 // PitchAnalyser.h:122-123 (s = 0 contributes 0)
             }
-            double inc = run;
+            double inc = (double) runf;
             #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
             {
@@ -649,31 +684,30 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
         unsigned first_cross = 0xffffffffu;
         {
-            double run = seg_exc;
+            double base = seg_exc;
             #pragma unroll
-            for (int w = 0; w < NW; ++w) if (w < warp) run += sm.pscan[w];
-            const float e_abs = 1.0e-6f * fabsf (sm.d0);
-            unsigned long long key = ((unsigned long long) __float_as_uint (100.0f) << 32) | 0xffffffffull;
-            #pragma unroll 4
+            for (int w = 0; w < NW; ++w) if (w < warp) base += sm.pscan[w];
+            // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
+            float sumf = (float) base;
+            float best = 100.0f; int best_s = -1;
+            #pragma unroll 8
             for (int j = 0; j < 16; ++j)
             {
                 const int s = 16 * t + j;
                 const float d = workf[17 * t + j];
                 const float a = __fmul_rn (__fmul_rn (d, d), (float) s);
-                if (s >= 1) run += (double) a;
-                const float sumf = (float) run;                                                  // :145 (fp32 running sum in the reference)
-                float c = (sumf != 0.0f) ? __fdiv_rn (a, sumf) : 0.0f;                           // :146-154
+                sumf += a;
+                float c = (sumf != 0.0f) ? __fdividef (a, sumf) : 0.0f;                          // :146-154
                 if (s == 0) c = 1.0f;                                                             // :141
-                const float u = (sumf != 0.0f) ? __fdividef ((2.0f * fabsf (d) * e_abs + e_abs * e_abs) * (float) s, sumf) : 0.0f;
                 workf[17 * t + j] = c;
-                workg[17 * t + j] = u;
+                workg[17 * t + j] = d;
                 if (s >= 2)
                 {
                     if (c < 0.01f && first_cross == 0xffffffffu) first_cross = (unsigned) s;      // :176
-                    const unsigned long long k2 = ((unsigned long long) __float_as_uint (c) << 32) | (unsigned) s;
-                    if (k2 < key && c >= 0.0f) key = k2;                                          // :171-175 first strict minimum
+                    if (c < best) { best = c; best_s = s; }                                       // :171-175 first strict minimum
                 }
             }
+            const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | (unsigned) best_s;
             const unsigned wfc = warp_minu (first_cross);
             const unsigned long long wkey = warp_minull (key);
             if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
@@ -704,33 +738,47 @@ k_analyse (const AnalyseParams p)
             hsum += sm.red[0][4][w]; hmax = fmax (hmax, sm.red[0][5][w]);
         }
         const bool crossed = (s0 != 0xffffffffu);
+        const float e_abs = 1.0e-6f * fabsf (sm.d0);
         {
             // phase C: end of the descending run that starts at s0 (:178-181), margins of the threshold tests,
-            // runner-up of the global minimum (margin only)
+            // runner-up of the global minimum (margin only).  Only the threads whose samples are involved do work.
             unsigned send = 0xffffffffu;
             float pm = 1.0f;
             float second = 100.0f;
-            const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
-            #pragma unroll 4
-            for (int j = 0; j < 16; ++j)
+            const int seg0 = 16 * t;
+            if (crossed)
             {
-                const unsigned s = (unsigned) (16 * t + j);
-                if (s < 2u) continue;
-                const float c = workf[17 * t + j];
-                if (crossed)
+                if (seg0 + 15 >= (int) s0)
                 {
-                    if (s <= s0) pm = fminf (pm, noisy_margin (c, workg[17 * t + j], 0.01f, 0.0f));
-                    if (s >= s0 && send == 0xffffffffu)
+                    #pragma unroll 1
+                    for (int j = max (0, (int) s0 - seg0); j < 16; ++j)
                     {
-                        const bool has_next = (s + 1u < (unsigned) N);
-                        const float nxt = has_next ? workf[phys ((int) s + 1)] : 0.0f;
-                        if (! (has_next && nxt < c)) send = s;
+                        const int s = seg0 + j;
+                        const bool has_next = (s + 1 < N);
+                        const float c = workf[17 * t + j];
+                        const float nxt = has_next ? workf[phys (s + 1)] : 0.0f;
+                        if (! (has_next && nxt < c)) { send = (unsigned) s; break; }
                     }
                 }
-                else
+                if (seg0 <= (int) s0)
                 {
-                    pm = fminf (pm, noisy_margin (c, workg[17 * t + j], 0.01f, 0.0f));
-                    if (s != gidx) second = fminf (second, c);
+                    #pragma unroll 1
+                    for (int j = (seg0 == 0 ? 2 : 0); j < 16 && seg0 + j <= (int) s0; ++j)
+                    {
+                        const float c = workf[17 * t + j];
+                        pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workg[17 * t + j], e_abs), 0.01f, 0.0f));
+                    }
+                }
+            }
+            else
+            {
+                const int gidx = (int) (unsigned) (gkey & 0xffffffffull);
+                #pragma unroll 2
+                for (int j = (seg0 == 0 ? 2 : 0); j < 16; ++j)
+                {
+                    const float c = workf[17 * t + j];
+                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workg[17 * t + j], e_abs), 0.01f, 0.0f));
+                    if (seg0 + j != gidx) second = fminf (second, c);
                 }
             }
             const unsigned wsend = warp_minu (send);
@@ -750,12 +798,18 @@ k_analyse (const AnalyseParams p)
                 // getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-203): the parabolic branch is unreachable
                 const int s_end = (int) send;
                 const int right = s_end + 1;
+                float c_prev = workf[phys ((int) s0)];
+                float u_prev = cnd_uncertainty (c_prev, workg[phys ((int) s0)], e_abs);
+                #pragma unroll 1
+                for (int s = (int) s0 + 1; s <= s_end + 1 && s < N; ++s)                          // every comparison the descent made
+                {
+                    const float c = workf[phys (s)];
+                    const float u = cnd_uncertainty (c, workg[phys (s)], e_abs);
+                    pm = fminf (pm, noisy_margin (c, u, c_prev, u_prev));
+                    c_prev = c; u_prev = u;
+                }
                 const float c_end = workf[phys (s_end)];
                 const float c_right = (right < N) ? workf[phys (right)] : 0.0f;      // cnd[N] = Im part of lag 0 = 0
-                #pragma unroll 1
-                for (int s = (int) s0; s < s_end; ++s)
-                    pm = fminf (pm, noisy_margin (workf[phys (s + 1)], workg[phys (s + 1)], workf[phys (s)], workg[phys (s)]));
-                if (right < N) pm = fminf (pm, noisy_margin (c_end, workg[phys (s_end)], c_right, workg[phys (right)]));
                 lag = (c_end <= c_right) ? (float) s_end : (float) right;
             }
             else
@@ -845,48 +899,34 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
         if (warp == 0)
         {
-            // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94)
-            float term = 0.0f; int hb = -1;
+            // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
+            // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3; the sums are warp reductions
+            double term = 0.0;
             if (lane < 18 && ! hsilent)
             {
-                const double fr = (lane < 15) ? f0 / ldexp (1.0, lane + 1) : f0 * (double) (lane - 14);
-                hb = (int) floor (fr / frpb);
-                if (hb >= 0 && hb < M)
+                const double fr = (lane < 15) ? f0 * ldexp_normal (0.5, -lane) : f0 * (double) (lane - 14);
+                const int hb = (int) floor (fr / frpb);
+                // a sub-octave landing in f0's own bin is skipped (:163-164); harmonics stop at the first bin >= M (:174-175),
+                // and since they ascend, skipping every bin >= M is the same
+                const bool use = (lane < 15) ? (hb != f0_bin && hb >= 0 && hb < M) : (hb >= 0 && hb < M);
+                if (use)
                 {
                     const int st = hb - 2 >= 0 ? hb - 2 : 0;
                     const int en = hb + 2 < M ? hb + 2 : M;
                     float mx = workf[hb];                                                         // :200-210
-                    for (int b = st; b < en; ++b) mx = fmaxf (mx, workf[b]);
-                    term = mx;
+                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, workf[bb]);
+                    term = (double) mx;
                 }
             }
-            if (lane < 18) { sm.her_terms[lane] = term; sm.her_bins[lane] = hb; }
-            __syncwarp();
+            double s3[3] = { term, lane == 16 ? term : 0.0, (lane == 15 || lane == 17) ? term : 0.0 };
+            warp_sum<3> (s3);
             if (lane == 0)
             {
                 double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f;
                 #pragma unroll
                 for (int w = 0; w < NW; ++w) { sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += sm.red[1][3][w]; pkm = fminf (pkm, sm.fmins[0][w]); }
-                double score = 0.0, even = 0.0, odd = 0.0;
-                if (! hsilent)
-                {
-                    #pragma unroll 1
-                    for (int l = 0; l < 15; ++l)
-                    {
-                        if (sm.her_bins[l] == f0_bin) continue;                                   // :163-164
-                        score += (double) sm.her_terms[l];
-                    }
-                    #pragma unroll 1
-                    for (int h = 1; h <= 3; ++h)
-                    {
-                        if (sm.her_bins[14 + h] >= M) break;                                      // :174-175
-                        const double bm = (double) sm.her_terms[14 + h];
-                        if (h % 2 == 0) even += bm; else odd += bm;
-                        score += bm;
-                    }
-                }
                 rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
-                rec->score = score; rec->even = even; rec->odd = odd;
+                rec->score = s3[0]; rec->even = s3[1]; rec->odd = s3[2];
                 rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
             }
         }
