@@ -181,7 +181,7 @@ template <int R1> struct Smem
     float2   tw2[D::TW2_LEN];
     float    ring[N];                // ring[a & (N-1)] = absolute sample a of the track
     float    specA[M];               // Re FFT (raw frame)        -> harmonic features
-    float    specB[2][M];            // Re FFT (windowed frame)   -> spectral features; [cur ^ 1] = previous non-silent frame
+    float    specB[M];               // Re FFT (windowed frame)   -> spectral features (the previous non-silent frame lives in HBM/L2: last_spec)
     double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
     double   scan_m[NW];             // flatness product scan, warp totals
     int      scan_e[NW];
@@ -216,7 +216,7 @@ __device__ __noinline__ V16 fft_core (V16 io, int m0)
 }
 
 template <int R1>
-__global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 2 : (R1 == 8 ? 4 : 8)))
+__global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 3 : (R1 == 8 ? 6 : 12)))
 k_analyse (const AnalyseParams p)
 {
     using D = FftDims<R1>;
@@ -248,7 +248,6 @@ k_analyse (const AnalyseParams p)
 
     for (int i = t; i < D::TW1_LEN; i += T) sm.tw1[i] = p.tw1[i];
     for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[i];
-    for (int i = t; i < M; i += T) { sm.specB[0][i] = 0.0f; sm.specB[1][i] = 0.0f; }
     if (t == 0) { mbar_init (&sm.mbar, 1); }
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -286,7 +285,9 @@ k_analyse (const AnalyseParams p)
     }
 
     uint32_t phase = 0;
-    int cur = 0;                      // specB[cur] receives this frame, specB[cur ^ 1] is the previous non-silent frame
+    // the chunk's running "previousBinMagnitudes" (as Re values): written after every non-silent frame, re-read by the
+    // same thread for the next frame's flux, and left behind for K2 as the chunk's last non-silent spectrum
+    float* prev_g = p.last_spec + (track * p.n_chunks + chunk) * (long) M;
     bool have_prev = false;           // false until the chunk's first non-silent frame (its flux is fixed up by K2)
     int first_nonsilent = -1;
     const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
@@ -332,6 +333,13 @@ k_analyse (const AnalyseParams p)
         }
         __syncthreads();
 
+        // previous non-silent spectrum of this thread's bins: issued now, consumed in pass 1 (L2 latency hidden by the split)
+        float4 p0 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f), p1 = p0;
+        if (have_prev)
+        {
+            p0 = *reinterpret_cast<const float4*> (&prev_g[b0]);
+            p1 = *reinterpret_cast<const float4*> (&prev_g[b0 + 4]);
+        }
         // split the packed spectrum: A = FFT (x), B = FFT (x w); keep Re A, Re B; Im B only for the slope quirk
         float rawmax = 0.0f;     // SpectralCharacteristics.h:153: max |buf[j]|, j < M, over the interleaved Re/Im floats = bins k < M/2
         #pragma unroll 4
@@ -344,7 +352,7 @@ k_analyse (const AnalyseParams p)
             const float reB = 0.5f * (zk.y + zn.y);
             const float imB = 0.5f * (zn.x - zk.x);
             sm.specA[k] = reA;
-            sm.specB[cur][k] = reB;
+            sm.specB[k] = reB;
             if (k < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
         }
         __syncthreads();
@@ -362,10 +370,8 @@ k_analyse (const AnalyseParams p)
         ME lprod = me_one();
         int e_budget = 0;                // sum of |exponent| over this thread's gated bins: bounds how far its running product can move
         {
-            const float4 c0 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0]);
-            const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[cur][b0 + 4]);
-            const float4 p0 = *reinterpret_cast<const float4*> (&sm.specB[cur ^ 1][b0]);
-            const float4 p1 = *reinterpret_cast<const float4*> (&sm.specB[cur ^ 1][b0 + 4]);
+            const float4 c0 = *reinterpret_cast<const float4*> (&sm.specB[b0]);
+            const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[b0 + 4]);
             cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
@@ -472,7 +478,7 @@ k_analyse (const AnalyseParams p)
                 #pragma unroll 1
                 for (int j = 0; j < 8; ++j)
                 {
-                    const double re = (double) sm.specB[cur][b0 + j];
+                    const double re = (double) sm.specB[b0 + j];
                     const double mg = re * re;
                     if (mg > eps)
                     {
@@ -527,7 +533,7 @@ k_analyse (const AnalyseParams p)
                     #pragma unroll 1
                     for (; (b & 3) != 0; ++b)
                     {
-                        const double re = (double) sm.specB[cur][b];
+                        const double re = (double) sm.specB[b];
                         const double mg = re * re;
                         if (mg > eps) prod *= mg;
                     }
@@ -535,7 +541,7 @@ k_analyse (const AnalyseParams p)
                     #pragma unroll 1
                     for (; b < M && prod != 0.0 && ! isinf (prod); b += 4)
                     {
-                        const float4 v4 = *reinterpret_cast<const float4*> (&sm.specB[cur][b]);
+                        const float4 v4 = *reinterpret_cast<const float4*> (&sm.specB[b]);
                         const double m0 = (double) v4.x * (double) v4.x, m1 = (double) v4.y * (double) v4.y;
                         const double m2 = (double) v4.z * (double) v4.z, m3 = (double) v4.w * (double) v4.w;
                         if (m0 > eps) prod *= m0;
@@ -547,11 +553,16 @@ k_analyse (const AnalyseParams p)
                 sm.flat_prod = prod;
             }
         }
-        if (! silent && ! have_prev)
+        if (! silent)
         {
-            float* fs = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
-            *reinterpret_cast<float4*> (&fs[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);
-            *reinterpret_cast<float4*> (&fs[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
+            if (! have_prev)
+            {
+                float* fs = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
+                *reinterpret_cast<float4*> (&fs[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);
+                *reinterpret_cast<float4*> (&fs[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
+            }
+            *reinterpret_cast<float4*> (&prev_g[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);       // :138 prev <- current
+            *reinterpret_cast<float4*> (&prev_g[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
         }
 
         // =========================== one-pole filter + window -> work array ============================
@@ -626,11 +637,7 @@ k_analyse (const AnalyseParams p)
             rec->centroid = centroid; rec->flat_margin = flat_margin; rec->flat_state = silent ? 3.0f : flat_state;
             rec->have_prev = have_prev ? 1.0f : 0.0f;
         }
-        if (! silent)
-        {
-            if (! have_prev) { have_prev = true; first_nonsilent = f; }
-            cur ^= 1;                                                                             // :138 prev <- current
-        }
+        if (! silent && ! have_prev) { have_prev = true; first_nonsilent = f; }
 
         // =========================== FFT2 (filtered, windowed) chained into FFT3 =======================
         #pragma unroll
@@ -935,11 +942,6 @@ k_analyse (const AnalyseParams p)
 
     // ---- chunk epilogue ----------------------------------------------------------------------------------
     if (t == 0) p.first_idx[track * p.n_chunks + chunk] = first_nonsilent;
-    if (have_prev)
-    {
-        float* ls = p.last_spec + (track * p.n_chunks + chunk) * (long) M;
-        for (int i = t; i < M; i += T) ls[i] = sm.specB[cur ^ 1][i];
-    }
     if (f_end == p.n_frames && p.tail_out != nullptr)
     {
         // the newest N - H samples of the stream become the next call's overlap

@@ -107,14 +107,16 @@ int ilog2 (int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 // twiddle tables in the layout fx_fft.cuh expects; evaluated in double, rounded to fp32 (as juce::FFT does)
 void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2)
 {
-    const int R1 = N / 256, ROW = 272;
+    const int R1 = N / 256;
     const double pi = 3.14159265358979323846;
-    tw1.assign ((size_t) (R1 - 1) * ROW, make_float2 (1.0f, 0.0f));
+    tw1.assign ((size_t) (R1 - 1) * 32, make_float2 (1.0f, 0.0f));
     for (int k1 = 1; k1 < R1; ++k1)
-        for (int m = 0; m < 256; ++m)
+        for (int i = 0; i < 16; ++i)
         {
-            const double ph = -2.0 * pi * (double) ((long) m * k1 % N) / (double) N;
-            tw1[(size_t) (k1 - 1) * ROW + (m + (m >> 4))] = make_float2 ((float) cos (ph), (float) sin (ph));
+            const double pa = -2.0 * pi * (double) ((long) 16 * i * k1 % N) / (double) N;     // W_N^(16 mh k1)
+            const double pb = -2.0 * pi * (double) (i * k1) / (double) N;                      // W_N^(ml k1)
+            tw1[(size_t) (k1 - 1) * 32 + i]      = make_float2 ((float) cos (pa), (float) sin (pa));
+            tw1[(size_t) (k1 - 1) * 32 + 16 + i] = make_float2 ((float) cos (pb), (float) sin (pb));
         }
     tw2.assign (15 * 16, make_float2 (1.0f, 0.0f));
     for (int k2 = 1; k2 < 16; ++k2)
@@ -329,7 +331,7 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
 
     fx_engine* e = new fx_engine();
     e->cfg = *cfg; e->N = N; e->H = H; e->M = N / 2; e->NB = N / H; e->log2_hop = ilog2 (H);
-    e->ctas_per_sm = (N == 4096) ? 2 : (N == 2048 ? 4 : 8);
+    e->ctas_per_sm = (N == 4096) ? 3 : (N == 2048 ? 6 : 12);
     const size_t T = (size_t) cfg->n_tracks;
 
 #define FX_CREATE(call) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) { fx_status st_ = FX_ERR_CUDA; fail (nullptr, st_, #call, ce_); free_engine (e); return FX_ERR_CUDA; } } while (0)

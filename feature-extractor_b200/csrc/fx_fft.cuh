@@ -11,7 +11,9 @@
 //   stage 3: (k1, k2)      : 16-point DFT over n3                         -> X[k]  in registers
 // The exchange buffer is addressed with a 17/16 skew (phys (a) = a + (a >> 4)) so that the row accesses
 // of stage 2, the column accesses of stage 3 and the stride-R1 natural-order store are all conflict free.
-// Twiddles come from tables evaluated in double on the host and rounded to fp32 (as JUCE does).
+// Twiddles come from small tables evaluated in double on the host and rounded to fp32 (as JUCE does); the stage-1
+// twiddle W_N^(m k1) is the product of two table entries, W_N^(16 mh k1) * W_N^(ml k1) with m = 16 mh + ml, which
+// keeps the tables at a few KB so that three CTAs fit on an SM.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -117,8 +119,9 @@ template <int R1> struct FftDims
     static constexpr int Q1      = 16 / R1;            // stage-1 butterflies per thread
     static constexpr int ROW     = 272;                // 256 * 17 / 16
     static constexpr int EX_LEN  = R1 * ROW;           // float2 elements in the exchange buffer (= N * 17 / 16)
-    static constexpr int TW1_LEN = (R1 - 1) * ROW;     // float2, tw1[(k1 - 1) * ROW + phys (m)] = W_N^(m k1)
-    static constexpr int TW2_LEN = 15 * 16;            // float2, tw2[(k2 - 1) * 16 + n3]        = W_256^(n3 k2)
+    static constexpr int TW1_LEN = (R1 - 1) * 32;      // float2, tw1[(k1 - 1) * 32 + mh]      = W_N^(16 mh k1)   (mh < 16)
+                                                       //         tw1[(k1 - 1) * 32 + 16 + ml] = W_N^(ml k1)      (ml < 16)
+    static constexpr int TW2_LEN = 15 * 16;            // float2, tw2[(k2 - 1) * 16 + n3]      = W_256^(n3 k2)
 };
 
 // butterfly index of stage 1 that thread t handles in its q-th slot group
@@ -137,13 +140,20 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
     for (int q = 0; q < D::Q1; ++q)
     {
         butterfly<R1, INV> (v + q * R1);
-        const int pm = phys (m0 + D::T * q);
+        const int m = m0 + D::T * q;
+        const int pm = phys (m);
+        const int mh = m >> 4, ml = 16 + (m & 15);
         #pragma unroll
         for (int s = 0; s < R1; ++s)
         {
             const int k1 = out_index<R1> (s);
             float2 val = v[q * R1 + s];
-            if (k1 > 0) val = cmulw<INV> (val, tw1[(k1 - 1) * D::ROW + pm]);
+            if (k1 > 0)
+            {
+                const float2 wa = tw1[(k1 - 1) * 32 + mh], wb = tw1[(k1 - 1) * 32 + ml];
+                const float2 w = make_float2 (wa.x * wb.x - wa.y * wb.y, wa.x * wb.y + wa.y * wb.x);
+                val = cmulw<INV> (val, w);
+            }
             ex[k1 * D::ROW + pm] = val;
         }
     }
