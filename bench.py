@@ -133,8 +133,8 @@ def run_reference_arm(args, rank, world):
     import oracle_util as ou
 
     cores = os.cpu_count() or 1
-    n_tracks = max(2 * cores, 16)
-    seconds = min(args.seconds, 4.0)
+    n_tracks = max(8 * cores, 64)
+    seconds = min(args.seconds, 10.0)
     S = (int(SR * seconds) // HOP) * HOP
     audio = ou.make_tracks(n_tracks, S, SR)
     for _ in range(min(args.warmup, 1)):

@@ -189,6 +189,7 @@ template <int R1> struct Smem
     unsigned long long keys[NW];
     unsigned ucodes[2][NW];
     float    fmins[2][NW];
+    float    fmaxs[NW];
     double   flat_prod;
     double   f0;
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
@@ -374,7 +375,8 @@ k_analyse (const AnalyseParams p)
             const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[b0 + 4]);
             cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
-            double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
+            double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0;
+            float maxre = 0.0f;
             unsigned fgap = 0xffffffffu;
             const float eps_f = (float) eps;
             double mprod = 1.0; int esum = 0;
@@ -401,12 +403,12 @@ k_analyse (const AnalyseParams p)
                 fgap = min (fgap, ulp_gap ((float) mg, eps_f));
                 const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
                 weighted += fc * mg;
-                maxmag = fmax (maxmag, mg);
+                maxre = fmaxf (maxre, fabsf (cr[j]));
             }
             lprod = me_from (mprod); lprod.e += esum;
             double s6[6] = { mag_sum, weighted, flux, lhr, flat_sum, count };
             warp_sum<6> (s6);
-            const double wmax = warp_max (maxmag);
+            const float wmax = warp_maxf (maxre);
             const float wraw = warp_maxf (rawmax);
             const float wmar = ulps_to_margin (warp_minu (fgap));
             // inclusive warp scan of the extended-range product, in bin order
@@ -425,28 +427,28 @@ k_analyse (const AnalyseParams p)
             {
                 #pragma unroll
                 for (int k = 0; k < 6; ++k) sm.red[1][k][warp] = s6[k];
-                sm.red[1][6][warp] = wmax;
+                sm.fmaxs[warp] = wmax;
                 sm.fmins[0][warp] = wmar;
                 sm.fmins[1][warp] = wraw;
             }
         }
         __syncthreads();
-        double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, maxmag = 0.0;
-        float flat_margin = 1.0f, rawmax_all = 0.0f;
-        ME total = me_one(), prefix = me_one();
+        double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0;
+        float flat_margin = 1.0f, rawmax_all = 0.0f, maxre_all = 0.0f;
+        ME prefix = me_one();
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
             mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w]; flux += sm.red[1][2][w];
             lhr += sm.red[1][3][w]; flat_sum += sm.red[1][4][w]; count += sm.red[1][5][w];
-            maxmag = fmax (maxmag, sm.red[1][6][w]);
+            maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
             flat_margin = fminf (flat_margin, sm.fmins[0][w]);
             rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
-            ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w];
-            if (w < warp) prefix = me_mul (prefix, wt);
-            total = me_mul (total, wt);
         }
+        #pragma unroll 1
+        for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
+        const double maxmag = (double) maxre_all * (double) maxre_all;
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
         const float centroid = (float) (weighted / mag_sum);                                      // :127
         const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
@@ -629,7 +631,13 @@ k_analyse (const AnalyseParams p)
             #pragma unroll
             for (int w = 0; w < NW; ++w) evar += sm.red[1][0][w];
             double product; float flat_state;
-            if (ev == 0xffffffffu) { product = ldexp_normal (total.m, total.e); flat_state = 0.0f; }
+            if (ev == 0xffffffffu)
+            {
+                ME total = me_one();
+                #pragma unroll 1
+                for (int w = 0; w < NW; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; total = me_mul (total, wt); }
+                product = ldexp_normal (total.m, total.e); flat_state = 0.0f;
+            }
             else { product = sm.flat_prod; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
             rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->flux = flux; rec->lhr = lhr;
             rec->flat_sum = flat_sum; rec->count = count; rec->product = product; rec->var = var; rec->sie = sie;
@@ -689,7 +697,8 @@ k_analyse (const AnalyseParams p)
             if (t == 0) sm.d0 = workf[0];
         }
         __syncthreads();
-        unsigned first_cross = 0xffffffffu;
+        unsigned first_cross = 0xffffffffu, nd_mask = 0u;
+        float c_last;
         {
             double base = seg_exc;
             #pragma unroll
@@ -697,6 +706,7 @@ k_analyse (const AnalyseParams p)
             // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
             float sumf = (float) base;
             float best = 100.0f; int best_s = -1;
+            float c_before = 0.0f;
             #pragma unroll 8
             for (int j = 0; j < 16; ++j)
             {
@@ -708,12 +718,15 @@ k_analyse (const AnalyseParams p)
                 if (s == 0) c = 1.0f;                                                             // :141
                 workf[17 * t + j] = c;
                 workg[17 * t + j] = d;
+                if (j > 0 && ! (c < c_before)) nd_mask |= 1u << (j - 1);          // the descent (:178) stops at j - 1
+                c_before = c;
                 if (s >= 2)
                 {
                     if (c < 0.01f && first_cross == 0xffffffffu) first_cross = (unsigned) s;      // :176
                     if (c < best) { best = c; best_s = s; }                                       // :171-175 first strict minimum
                 }
             }
+            c_last = c_before;
             const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | (unsigned) best_s;
             const unsigned wfc = warp_minu (first_cross);
             const unsigned long long wkey = warp_minull (key);
@@ -725,25 +738,26 @@ k_analyse (const AnalyseParams p)
             const float4 a0v = *reinterpret_cast<const float4*> (&sm.specA[b0]);
             const float4 a1v = *reinterpret_cast<const float4*> (&sm.specA[b0 + 4]);
             ar[0] = a0v.x; ar[1] = a0v.y; ar[2] = a0v.z; ar[3] = a0v.w; ar[4] = a1v.x; ar[5] = a1v.y; ar[6] = a1v.z; ar[7] = a1v.w;
-            double hsum = 0.0, hmax = 0.0;
+            double hsum = 0.0; float hmaxre = 0.0f;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { const double re = (double) ar[j]; const double mg = re * re; hsum += mg; hmax = fmax (hmax, mg); }
+            for (int j = 0; j < 8; ++j) { const double re = (double) ar[j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[j])); }
             double s1[1] = { hsum };
             warp_sum<1> (s1);
-            const double wm = warp_max (hmax);
-            if (lane == 0) { sm.red[0][4][warp] = s1[0]; sm.red[0][5][warp] = wm; }
+            const float wm = warp_maxf (hmaxre);
+            if (lane == 0) { sm.red[0][4][warp] = s1[0]; sm.fmaxs[warp] = wm; }
         }
         __syncthreads();
         unsigned s0 = 0xffffffffu;
         unsigned long long gkey = ~0ull;
-        double hsum = 0.0, hmax = 0.0;
+        double hsum = 0.0; float hmaxre = 0.0f;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
             s0 = min (s0, sm.ucodes[1][w]);
             gkey = sm.keys[w] < gkey ? sm.keys[w] : gkey;
-            hsum += sm.red[0][4][w]; hmax = fmax (hmax, sm.red[0][5][w]);
+            hsum += sm.red[0][4][w]; hmaxre = fmaxf (hmaxre, sm.fmaxs[w]);
         }
+        const double hmax = (double) hmaxre * (double) hmaxre;
         const bool crossed = (s0 != 0xffffffffu);
         const float e_abs = 1.0e-6f * fabsf (sm.d0);
         {
@@ -757,14 +771,15 @@ k_analyse (const AnalyseParams p)
             {
                 if (seg0 + 15 >= (int) s0)
                 {
-                    #pragma unroll 1
-                    for (int j = max (0, (int) s0 - seg0); j < 16; ++j)
+                    const int j0 = max (0, (int) s0 - seg0);
+                    const unsigned m = nd_mask >> j0;                                  // positions j0 .. 14 of this segment
+                    if (m != 0u) send = (unsigned) (seg0 + j0 + __ffs ((int) m) - 1);
+                    else
                     {
-                        const int s = seg0 + j;
+                        const int s = seg0 + 15;                                        // position 15 looks into the next segment
                         const bool has_next = (s + 1 < N);
-                        const float c = workf[17 * t + j];
                         const float nxt = has_next ? workf[phys (s + 1)] : 0.0f;
-                        if (! (has_next && nxt < c)) { send = (unsigned) s; break; }
+                        if (! (has_next && nxt < c_last)) send = (unsigned) s;
                     }
                 }
                 if (seg0 <= (int) s0)

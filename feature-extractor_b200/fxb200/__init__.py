@@ -233,6 +233,17 @@ class Engine:
         return int(self.lib.fx_kernel_launches(self._h))
 
 
+def shard_tracks(n_tracks: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous track range [first, first + count) of `rank` when n_tracks are sharded over world_size GPUs.
+    Tracks are independent (AnalyserTrackController owns all per-track state, AnalyserTrackController.h:199-210),
+    so the multi-GPU path is a partition with no exchange step."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad world_size / rank")
+    base, extra = divmod(n_tracks, world_size)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
 def measure_fp32_peak(device: int = 0) -> float:
     lib = load_library()
     tf = c_double(0)

@@ -64,6 +64,23 @@ def test_parity_against_oracle(fx, oracle, N, H, sr, T, sec):
     assert_parity(ou.compare(g, o), f"N={N} H={H} T={T} oracle={oracle.kind}")
 
 
+def test_config2_full_size(fx, oracle):
+    """BASELINE.json configs[1] in full: 64 tracks x 60 s at 48 kHz, 2048-point frames, hop 512 -> 5625 frames per
+    track, 360 000 frames, every one of the 12 features of every frame against the oracle."""
+    N, H, sr, T = 2048, 512, 48000.0, 64
+    S = 60 * 48000
+    audio = ou.make_tracks(T, S, sr)
+    with fx.Engine(n_tracks=T, window=N, hop=H, sample_rate=sr) as e:
+        g = e.analyse_host(audio)
+    assert g["frames"] == 5625
+    o = oracle.analyse(audio, window=N, hop=H, sample_rate=sr)
+    res = ou.compare(g, o)
+    assert_parity(res, f"configs[1] full size, oracle={oracle.kind}", max_exempt_frac=0.002)
+    # onset flags: exact except exempt frames
+    on_g, on_o = g["raw"][..., 0], o["raw"][..., 0]
+    assert on_o.sum() > 1000 and abs(float(on_g.sum() - on_o.sum())) <= 5
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_parity_against_golden_fixtures(fx, path):
     z = np.load(path, allow_pickle=True)
