@@ -101,6 +101,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(args):
+    """DRAM bytes per k_analyse launch from the committed ncu --set full capture (only valid for the default workload)."""
+    p = os.path.join(ROOT, "profiles", "k_analyse_traffic.json")
+    if args.tracks == 4096 and args.seconds == 10.0 and os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -277,7 +288,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_cpu_tracks = min(T, max(4 * cores, 32))
+        n_cpu_tracks = min(T, max(16 * cores, 64))
         sample_audio = audio[:n_cpu_tracks].cpu().numpy()
         rate, kind, frames, dt = cpu_reference_rate(sample_audio, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
@@ -285,6 +296,7 @@ def main():
 
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
+        traffic = measured_traffic(args)
         k1_s = (ms_k1 * 1e-3) / max(ncalls, 1)                       # average k_analyse launch duration, CUDA events on its stream
         flops = algorithmic_flops_per_frame(WINDOW) * frames_per_step
         byts = algorithmic_bytes_per_frame(HOP) * frames_per_step
@@ -294,12 +306,12 @@ def main():
             "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, world),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "k_analyse<16>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": traffic,
                          "peak_source": "FMA microbenchmark on this GPU (fx_measure_fp32_peak), measured",
                          "note": "binding roofline per north_star: min (HBM_BW / B, FP32_peak / F) is the FP32 term for this path",
                          "kernel_ms": k1_s * 1e3, "kernel_share_of_step": ms_k1 / ms_total if ms_total else None},
             "roofline_hbm": {"bound": "hbm", "kernel": "k_analyse<16>", "achieved": byts / k1_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": byts / k1_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src},
+                             "frac": byts / k1_s / 1e9 / hbm_peak, "traffic": traffic, "algorithmic_bytes": byts, "peak_source": hbm_src},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
