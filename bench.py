@@ -31,6 +31,7 @@ import sys
 import tempfile
 import time
 
+_REAL_STDOUT = None
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(ROOT, "feature-extractor_b200"), os.path.join(ROOT, "tests")]
 
@@ -45,6 +46,12 @@ def algorithmic_bytes_per_frame(hop: int) -> float:
 
 def algorithmic_flops_per_frame(n: int) -> float:
     return 10.0 * n * math.log2(n) + 48.0 * n   # four real N-point transforms + O(N) feature work
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def config_dict(args, n_gpus):
@@ -166,7 +173,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -186,6 +193,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner, ...) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -314,7 +326,7 @@ def main():
                              "frac": byts / k1_s / 1e9 / hbm_peak, "traffic": traffic, "algorithmic_bytes": byts, "peak_source": hbm_src},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
