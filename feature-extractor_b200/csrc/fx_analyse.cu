@@ -76,7 +76,7 @@ __device__ __forceinline__ float relmargin_d (double a, double b)
     const float m = (float) fmax (fabs (a), fabs (b));
     return (m > 0.0f) ? __fdividef ((float) fabs (a - b), m) : 0.0f;
 }
-// margin of a comparison between cnd values with fp32 uncertainties ua, ub (see estimate_pitch in oracle/fx_oracle.c)
+// margin of a comparison between cnd values with fp32 uncertainties ua, ub (the CPU checker computes the same margin in its pitch estimator)
 __device__ __forceinline__ float noisy_margin (float a, float ua, float b, float ub)
 {
     const float gap = fabsf (a - b) - (ua + ub);
