@@ -105,6 +105,12 @@ __device__ __forceinline__ float ulps_to_margin (unsigned u)
 {
     return u >= (1u << 24) ? 1.0f : (float) u * (1.0f / 16777216.0f);
 }
+__device__ __forceinline__ float rcp_approx (float x)
+{
+    float r;
+    asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
 {
     return (m * 2.0) * __hiloint2double ((e - 1 + 1023) << 20, 0);
@@ -294,6 +300,10 @@ k_analyse (const AnalyseParams p)
     const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
     const int b0 = 8 * t;                                           // this thread's 8 consecutive bins
     const double inv_m = 1.0 / (double) M;                          // exact: M is a power of two
+    const float t2n = (float) t * (2.0f / N);                       // window ramp at this thread's offset (exact)
+    // the same ramp over this thread's 16 consecutive samples (filter / pitch layout): w = wseg_0 + j wseg_d
+    const float wseg_0 = (16 * t < M) ? (float) (16 * t) * (2.0f / N) : 1.0f - (float) (16 * t - M) * (2.0f / N);
+    const float wseg_d = (16 * t < M) ? (2.0f / N) : -(2.0f / N);
 
     #pragma unroll 1
     for (int f = f_begin; f < f_end; ++f)
@@ -308,20 +318,24 @@ k_analyse (const AnalyseParams p)
         // =========================== FFT1: z = x + i (x * bartlett) ====================================
         V16 io;
         {
-            double rms_part = 0.0;
+            // getRMSLevel squares in fp32 and sums in fp64; here the 16 squares of a thread are summed in fp32 first
+            // (two chains) and the 256 x 8 partials in fp64: 1e-7 relative on a feature compared at 1e-4
+            float sq0 = 0.0f, sq1 = 0.0f;
+            const int rb = (int) ((a0 + t) & (N - 1));
             #pragma unroll
             for (int q = 0; q < Q1; ++q)
                 #pragma unroll
                 for (int n1 = 0; n1 < R1; ++n1)
                 {
-                    const int n = n1 * 256 + t + T * q;
-                    const float x = __fmul_rn (sm.ring[(int) ((a0 + n) & (N - 1))], gain);       // AudioDataCollector.h:88
-                    // RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N (exact in fp32)
-                    const float w = (n < M) ? (float) n * (2.0f / N) : 1.0f - (float) (n - M) * (2.0f / N);
+                    const int c = n1 * 256 + T * q;                                               // n = c + t, c a multiple of T
+                    const float x = __fmul_rn (sm.ring[(rb + c) & (N - 1)], gain);                // AudioDataCollector.h:88
+                    // RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N; every term is a multiple
+                    // of 2/N in [0, 1], so constant + t * 2/N is exact in fp32
+                    const float w = (c < M) ? (float) c * (2.0f / N) + t2n : (1.0f - (float) (c - M) * (2.0f / N)) - t2n;
                     io.v[q * R1 + n1] = make_float2 (x, __fmul_rn (x, w));
-                    rms_part += (double) __fmul_rn (x, x);                                       // getRMSLevel: fp32 square, fp64 sum
+                    if ((n1 & 1) == 0) sq0 = fmaf (x, x, sq0); else sq1 = fmaf (x, x, sq1);
                 }
-            double r1[1] = { rms_part };
+            double r1[1] = { (double) (sq0 + sq1) };
             warp_sum<1> (r1);
             if (lane == 0) sm.red[0][0][warp] = r1[0];
         }
@@ -362,8 +376,9 @@ k_analyse (const AnalyseParams p)
         double rms_sum = 0.0;
         #pragma unroll
         for (int w = 0; w < NW; ++w) rms_sum += sm.red[0][0][w];
-        const float rms = (float) sqrt (rms_sum / (double) N);
-        const float log_rms = (float) log10 ((double) __fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));
+        // K1b recomputes both in double for the RMS feature; here they only set the flatness gate, whose margin is reported
+        const float rms = __fsqrt_rn ((float) (rms_sum * (1.0 / (double) N)));
+        const float log_rms = log10f (__fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));
         const double eps = 0.01 * (double) log_rms;                                               // SpectralCharacteristics.h:108
 
         // =========================== spectral features, pass 1 ========================================
@@ -433,16 +448,16 @@ k_analyse (const AnalyseParams p)
             }
         }
         __syncthreads();
-        double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0;
-        float flat_margin = 1.0f, rawmax_all = 0.0f, maxre_all = 0.0f;
+        // every thread needs the magnitude sum, the centroid and the maxima; flux, the low-energy sum, the flatness sums
+        // and the gate margin only go into the record and are combined by thread 0 when it writes it
+        double mag_sum = 0.0, weighted = 0.0;
+        float rawmax_all = 0.0f, maxre_all = 0.0f;
         ME prefix = me_one();
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-            mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w]; flux += sm.red[1][2][w];
-            lhr += sm.red[1][3][w]; flat_sum += sm.red[1][4][w]; count += sm.red[1][5][w];
+            mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w];
             maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
-            flat_margin = fminf (flat_margin, sm.fmins[0][w]);
             rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
         }
         #pragma unroll 1
@@ -505,12 +520,12 @@ k_analyse (const AnalyseParams p)
             }
         }
         __syncthreads();
-        double var = 0.0, se = 0.0, sie = 0.0;
+        double se = 0.0;
         unsigned ev = 0xffffffffu;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-            var += sm.red[0][1][w]; se += sm.red[0][2][w]; sie += sm.red[0][3][w];
+            se += sm.red[0][2][w];
             ev = min (ev, sm.ucodes[0][w]);
         }
         const double mean_e = se * inv_m;                                                         // :177
@@ -569,38 +584,54 @@ k_analyse (const AnalyseParams p)
 
         // =========================== one-pole filter + window -> work array ============================
         // AudioFilter::filterAudio (RealTimeAudioAnalysis.h:106-125): y[0] = x[0]; y[n] = (pi/2) x[n] + e^(-pi/2) y[n-1].
-        // Each thread owns 16 consecutive samples; the recurrence is warmed up over the 16 samples before them
-        // (e^(-pi/2)^16 = 1.2e-11 of the state survives, far below fp32 resolution), then run in the reference's
-        // arithmetic.  The work array is free: the spectrum split was the last reader of the exchange buffer.
+        // Each thread owns 16 consecutive samples: it runs the recurrence from a zero state over them, takes the state
+        // entering its segment from its left neighbour's zero-state end value (what that misses is e^(-pi/2)^16 = 1.2e-11
+        // of the state, far below fp32 resolution) and adds its decaying contribution e^(-pi/2)^(j+1) y_in.  FMAs and
+        // the folded gain differ from the reference's separate roundings by an ulp, well inside the rounding of the FFT
+        // this feeds.  The work array is free: the spectrum split was the last reader of the exchange buffer.
         {
             const int n0 = 16 * t;
             const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
-            float xs[16];
+            const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
+            float ys[16];
             #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
                 const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
-                xs[4 * q] = __fmul_rn (x4.x, gain); xs[4 * q + 1] = __fmul_rn (x4.y, gain);
-                xs[4 * q + 2] = __fmul_rn (x4.z, gain); xs[4 * q + 3] = __fmul_rn (x4.w, gain);
+                ys[4 * q] = x4.x; ys[4 * q + 1] = x4.y; ys[4 * q + 2] = x4.z; ys[4 * q + 3] = x4.w;
             }
-            float y = 0.0f;
-            // warm-up over the previous thread's samples (lane 0 of a warp fetches them itself)
-            const int rp = (int) ((a0 + n0 - 16) & (N - 1));
+            float y = (t == 0) ? __fmul_rn (ys[0], gain) : __fmul_rn (ys[0], c1g);               // y[0] = x[0]
+            ys[0] = y;
+            #pragma unroll
+            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (ys[j], c1g)); ys[j] = y; }
+            float yin = __shfl_up_sync (0xffffffffu, y, 1);
+            if (lane == 0)
+            {
+                yin = 0.0f;
+                if (t != 0)
+                {
+                    // the left neighbour lives in another warp: warm up over its last 12 samples (e^(-pi/2)^12 = 6.5e-9)
+                    const int rp = (int) ((a0 + n0 - 12) & (N - 1));
+                    #pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                    {
+                        const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[rp + 4 * q]);
+                        yin = fmaf (c2, yin, __fmul_rn (x4.x, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.y, c1g));
+                        yin = fmaf (c2, yin, __fmul_rn (x4.z, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.w, c1g));
+                    }
+                }
+            }
+            // e^(-pi/2 (j+1)): the filter constant is fixed by AudioFilter::m = 2 (RealTimeAudioAnalysis.h:127)
+            constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
+                                           8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,
+                                           3.132781128e-08f, 6.512412136e-09f };
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                float x = __shfl_up_sync (0xffffffffu, xs[j], 1);
-                if (lane == 0) x = __fmul_rn (sm.ring[rp + j], gain);
-                y = (n0 - 16 + j == 0) ? x : __fadd_rn (__fmul_rn (p.iir_c1, x), __fmul_rn (p.iir_c2, y));
-            }
-            if (t == 0) y = 0.0f;
-            #pragma unroll
-            for (int j = 0; j < 16; ++j)
-            {
-                const int n = n0 + j;
-                y = (n == 0) ? xs[j] : __fadd_rn (__fmul_rn (p.iir_c1, xs[j]), __fmul_rn (p.iir_c2, y));
-                const float w = (n < M) ? (float) n * (2.0f / N) : 1.0f - (float) (n - M) * (2.0f / N);
-                workf[17 * t + j] = __fmul_rn (y, w);                                             // phys (16 t + j)
+                if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
+                // Bartlett ramp at n = n0 + j: all 16 samples lie in the same half, the ramp values are exact in fp32
+                const float w = fmaf ((float) j, wseg_d, wseg_0);
+                workf[17 * t + j] = __fmul_rn (ys[j], w);                                         // phys (16 t + j)
             }
         }
         __syncthreads();                                            // ring is free: prefetch the next hop
@@ -627,9 +658,17 @@ k_analyse (const AnalyseParams p)
         // spectral record (flat_prod and the pass-3 partials were published by the barrier above)
         if (t == 0)
         {
-            double evar = 0.0;
+            // the pass-1 slots red[1][2..5], fmins[0] and the pass-2 slots red[0][1], red[0][3] are not reused before the next frame
+            double evar = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, var = 0.0, sie = 0.0;
+            float flat_margin = 1.0f;
             #pragma unroll
-            for (int w = 0; w < NW; ++w) evar += sm.red[1][0][w];
+            for (int w = 0; w < NW; ++w)
+            {
+                evar += sm.red[1][0][w];
+                flux += sm.red[1][2][w]; lhr += sm.red[1][3][w]; flat_sum += sm.red[1][4][w]; count += sm.red[1][5][w];
+                var += sm.red[0][1][w]; sie += sm.red[0][3][w];
+                flat_margin = fminf (flat_margin, sm.fmins[0][w]);
+            }
             double product; float flat_state;
             if (ev == 0xffffffffu)
             {
@@ -674,15 +713,18 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
+        // workf holds d[s] (kept for the margins), workg receives cnd[s]; each thread owns s = 16 t .. 16 t + 15
+        float av[16];                                                                             // ac[s] = d^2 s (PitchAnalyser.h:122-123)
         double seg_exc;
         {
+            const float s0f = (float) (16 * t);
             float runf = 0.0f;
-            #pragma unroll 8
+            #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                const int s = 16 * t + j;
                 const float d = workf[17 * t + j];
-                runf += __fmul_rn (__fmul_rn (d, d), (float) s);                                 // PitchAnalyser.h:122-123 (s = 0 contributes 0)
+                av[j] = __fmul_rn (__fmul_rn (d, d), s0f + (float) j);                            // s = 0 contributes 0
+                runf += av[j];
             }
             double inc = (double) runf;
             #pragma unroll
@@ -705,29 +747,28 @@ k_analyse (const AnalyseParams p)
             for (int w = 0; w < NW; ++w) if (w < warp) base += sm.pscan[w];
             // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
             float sumf = (float) base;
-            float best = 100.0f; int best_s = -1;
+            float best = 100.0f; int best_j = -1;
+            unsigned cross = 0u;
             float c_before = 0.0f;
-            #pragma unroll 8
+            #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                const int s = 16 * t + j;
-                const float d = workf[17 * t + j];
-                const float a = __fmul_rn (__fmul_rn (d, d), (float) s);
-                sumf += a;
-                float c = (sumf != 0.0f) ? __fdividef (a, sumf) : 0.0f;                          // :146-154
-                if (s == 0) c = 1.0f;                                                             // :141
-                workf[17 * t + j] = c;
-                workg[17 * t + j] = d;
+                sumf += av[j];
+                float c = (sumf != 0.0f) ? __fmul_rn (av[j], rcp_approx (sumf)) : 0.0f;          // :146-154
+                if (j == 0 && t == 0) c = 1.0f;                                                   // :141
+                workg[17 * t + j] = c;
                 if (j > 0 && ! (c < c_before)) nd_mask |= 1u << (j - 1);          // the descent (:178) stops at j - 1
                 c_before = c;
-                if (s >= 2)
+                if (j >= 2 || t != 0)                                                             // the search starts at s = 2 (:169)
                 {
-                    if (c < 0.01f && first_cross == 0xffffffffu) first_cross = (unsigned) s;      // :176
-                    if (c < best) { best = c; best_s = s; }                                       // :171-175 first strict minimum
+                    if (c < 0.01f) cross |= 1u << j;                                              // :176
+                    if (c < best) { best = c; best_j = j; }                                       // :171-175 first strict minimum
                 }
             }
             c_last = c_before;
-            const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | (unsigned) best_s;
+            if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
+            const unsigned best_s = best_j < 0 ? 0xffffffffu : (unsigned) (16 * t + best_j);
+            const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | best_s;
             const unsigned wfc = warp_minu (first_cross);
             const unsigned long long wkey = warp_minull (key);
             if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
@@ -778,7 +819,7 @@ k_analyse (const AnalyseParams p)
                     {
                         const int s = seg0 + 15;                                        // position 15 looks into the next segment
                         const bool has_next = (s + 1 < N);
-                        const float nxt = has_next ? workf[phys (s + 1)] : 0.0f;
+                        const float nxt = has_next ? workg[phys (s + 1)] : 0.0f;
                         if (! (has_next && nxt < c_last)) send = (unsigned) s;
                     }
                 }
@@ -787,8 +828,8 @@ k_analyse (const AnalyseParams p)
                     #pragma unroll 1
                     for (int j = (seg0 == 0 ? 2 : 0); j < 16 && seg0 + j <= (int) s0; ++j)
                     {
-                        const float c = workf[17 * t + j];
-                        pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workg[17 * t + j], e_abs), 0.01f, 0.0f));
+                        const float c = workg[17 * t + j];
+                        pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
                     }
                 }
             }
@@ -798,8 +839,8 @@ k_analyse (const AnalyseParams p)
                 #pragma unroll 2
                 for (int j = (seg0 == 0 ? 2 : 0); j < 16; ++j)
                 {
-                    const float c = workf[17 * t + j];
-                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workg[17 * t + j], e_abs), 0.01f, 0.0f));
+                    const float c = workg[17 * t + j];
+                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
                     if (seg0 + j != gidx) second = fminf (second, c);
                 }
             }
@@ -809,7 +850,7 @@ k_analyse (const AnalyseParams p)
             if (lane == 0) { sm.ucodes[0][warp] = wsend; sm.fmins[0][warp] = wpm; sm.fmins[1][warp] = wsec; }
         }
         __syncthreads();
-        if (t == 0)
+        if (warp == 0)
         {
             unsigned send = 0xffffffffu; float pm = 1.0f, second = 100.0f;
             #pragma unroll
@@ -817,21 +858,22 @@ k_analyse (const AnalyseParams p)
             float lag;
             if (crossed)
             {
-                // getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-203): the parabolic branch is unreachable
+                // getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-203): the parabolic branch is unreachable.
+                // The margins of every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1, one per lane.
                 const int s_end = (int) send;
-                const int right = s_end + 1;
-                float c_prev = workf[phys ((int) s0)];
-                float u_prev = cnd_uncertainty (c_prev, workg[phys ((int) s0)], e_abs);
+                const int s_hi = min (s_end + 1, N - 1);
                 #pragma unroll 1
-                for (int s = (int) s0 + 1; s <= s_end + 1 && s < N; ++s)                          // every comparison the descent made
+                for (int s = (int) s0 + 1 + lane; s <= s_hi; s += 32)
                 {
-                    const float c = workf[phys (s)];
-                    const float u = cnd_uncertainty (c, workg[phys (s)], e_abs);
-                    pm = fminf (pm, noisy_margin (c, u, c_prev, u_prev));
-                    c_prev = c; u_prev = u;
+                    const float c = workg[phys (s)], cp = workg[phys (s - 1)];
+                    const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
+                    const float up = cnd_uncertainty (cp, workf[phys (s - 1)], e_abs);
+                    pm = fminf (pm, noisy_margin (c, u, cp, up));
                 }
-                const float c_end = workf[phys (s_end)];
-                const float c_right = (right < N) ? workf[phys (right)] : 0.0f;      // cnd[N] = Im part of lag 0 = 0
+                pm = warp_minf (pm);
+                const int right = s_end + 1;
+                const float c_end = workg[phys (s_end)];
+                const float c_right = (right < N) ? workg[phys (right)] : 0.0f;      // cnd[N] = Im part of lag 0 = 0
                 lag = (c_end <= c_right) ? (float) s_end : (float) right;
             }
             else
@@ -840,8 +882,11 @@ k_analyse (const AnalyseParams p)
                 lag = (gidx == 0xffffffffu) ? -1.0f : (float) gidx;                               // :165,188
                 pm = fminf (pm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
             }
-            sm.f0 = (nyquist * 2.0) / (double) lag;                                               // :57
-            rec->lag = lag; rec->pitch_margin = pm;
+            if (lane == 0)
+            {
+                sm.f0 = (nyquist * 2.0) / (double) lag;                                           // :57
+                rec->lag = lag; rec->pitch_margin = pm;
+            }
         }
         __syncthreads();
 

@@ -13,7 +13,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_long, c_uint64
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfxb200.so")
+# FXB200_LIB selects another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("FXB200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfxb200.so")
 
 NUM_FEATURES = 12
 NUM_DIAG = 10
