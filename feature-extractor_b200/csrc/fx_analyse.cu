@@ -10,13 +10,14 @@
 //
 // Data movement: the hop's new samples arrive by cp.async.bulk (TMA bulk copy, mbarrier completion) into a
 // shared-memory ring holding the N-sample window, so each input sample crosses HBM once per chunk; the next
-// hop is prefetched while the current frame's FFTs run.  Three complex FFTs per frame, all through ONE
-// out-of-line copy of the FFT code (the kernel is instruction-cache bound otherwise):
-//   FFT1  z = x + i (x * w)      -> Re A (raw frame), Re B / Im B (windowed frame) by conjugate symmetry
-//   FFT2  c = onepole (x) * w    -> P[k] = Re C[k]^2
-//   FFT3  forward transform of the real sequence P, chained in registers from FFT2: its real part equals the
-//         real part of the inverse transform the reference performs (PitchAnalyser.h:120), which is all that
-//         can reach the lag search (PitchAnalyser.h:163)
+// hop is prefetched while the current frame's second transform and the pitch / harmonic passes run.
+// The reference runs four real-input transforms per hop; here they are packed into TWO complex FFTs, both through
+// ONE out-of-line copy of the FFT code (the kernel is instruction-cache bound otherwise):
+//   FFT-alpha  z = x w + i onepole (x) w   -> B = FFT (x w): Re B (+ Im B for the slope quirk), C: P[k] = Re C[k]^2,
+//              separated by conjugate symmetry for each thread's own 8 consecutive bins
+//   FFT-beta   z = x + i 2^k P             -> Re Z = Re A (raw frame, harmonic features); Im Z[s] + Im Z[N-s] = 2^(k+1) D[s],
+//              D = FFT (P) real and even = N x the real part of the inverse transform the reference performs
+//              (PitchAnalyser.h:120), which is all that can reach the lag search (PitchAnalyser.h:163)
 // K1 leaves the per-frame sums in a FrameRec; K1b (one thread per frame) applies the scalar tail of the
 // reference (pow / log10 / sqrt, clamps, gates) so that no serial libm code sits inside the frame loop.
 // All feature reductions accumulate in fp64 like the reference.  No tensor cores: nothing here is a GEMM.
@@ -150,6 +151,12 @@ __device__ __forceinline__ double warp_max (double v)
     for (int off = 16; off > 0; off >>= 1) v = fmax (v, __shfl_xor_sync (0xffffffffu, v, off));
     return v;
 }
+__device__ __forceinline__ float warp_sumf (float v)
+{
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync (0xffffffffu, v, off);
+    return v;
+}
 __device__ __forceinline__ float warp_minf (float v)
 {
     #pragma unroll
@@ -186,8 +193,7 @@ template <int R1> struct Smem
     float2   tw1[D::TW1_LEN];
     float2   tw2[D::TW2_LEN];
     float    ring[N];                // ring[a & (N-1)] = absolute sample a of the track
-    float    specA[M];               // Re FFT (raw frame)        -> harmonic features
-    float    specB[M];               // Re FFT (windowed frame)   -> spectral features (the previous non-silent frame lives in HBM/L2: last_spec)
+    float    pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
     double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
     double   scan_m[NW];             // flatness product scan, warp totals
     int      scan_e[NW];
@@ -196,8 +202,10 @@ template <int R1> struct Smem
     unsigned ucodes[2][NW];
     float    fmins[2][NW];
     float    fmaxs[NW];
+    float    psums[NW];
+    float    pmins[2][NW];           // pitch margin / runner-up partials
+    unsigned short ndm[T];           // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178)
     double   flat_prod;
-    double   f0;
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     uint64_t mbar;
 };
@@ -233,6 +241,7 @@ k_analyse (const AnalyseParams p)
     S& sm = *reinterpret_cast<S*> (fx_smem_raw);
     float* workf = reinterpret_cast<float*> (sm.ex);          // fp32 view, skewed index phys (n)
     float* workg = workf + D::EX_LEN;                          // second fp32 array in the same buffer
+    float* specb = workf;                                      // Re B in bin order (unskewed) while the spectral passes run
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long cta = blockIdx.x;
@@ -315,12 +324,74 @@ k_analyse (const AnalyseParams p)
         mbar_wait (&sm.mbar, phase);
         phase ^= 1u;
 
-        // =========================== FFT1: z = x + i (x * bartlett) ====================================
+        // =========================== one-pole filter + window -> work array ============================
+        // AudioFilter::filterAudio (RealTimeAudioAnalysis.h:106-125): y[0] = x[0]; y[n] = (pi/2) x[n] + e^(-pi/2) y[n-1].
+        // Each thread owns 16 consecutive samples: it runs the recurrence from a zero state over them, takes the state
+        // entering its segment from its left neighbour's zero-state end value (what that misses is e^(-pi/2)^16 = 1.2e-11
+        // of the state, far below fp32 resolution) and adds its decaying contribution e^(-pi/2)^(j+1) y_in.  FMAs and
+        // the folded gain differ from the reference's separate roundings by an ulp, well inside the rounding of the FFT
+        // this feeds.  The work array is free: the previous frame ended with a barrier.  The same pass over the raw
+        // samples takes the sum of squares for the RMS (getRMSLevel: fp32 squares, fp64 sum; here 16 squares are summed in
+        // fp32 first, 1e-7 relative on a feature compared at 1e-4).
+        {
+            const int n0 = 16 * t;
+            const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
+            const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
+            float ys[16];
+            float sq0 = 0.0f, sq1 = 0.0f;
+            #pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
+                ys[4 * q] = x4.x; ys[4 * q + 1] = x4.y; ys[4 * q + 2] = x4.z; ys[4 * q + 3] = x4.w;
+                sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
+            }
+            {
+                double r1[1] = { (double) (sq0 + sq1) * ((double) gain * (double) gain) };       // AudioDataCollector.h:88 applies the gain
+                warp_sum<1> (r1);
+                if (lane == 0) sm.red[0][0][warp] = r1[0];
+            }
+            float y = (t == 0) ? __fmul_rn (ys[0], gain) : __fmul_rn (ys[0], c1g);               // y[0] = x[0]
+            ys[0] = y;
+            #pragma unroll
+            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (ys[j], c1g)); ys[j] = y; }
+            float yin = __shfl_up_sync (0xffffffffu, y, 1);
+            if (lane == 0)
+            {
+                yin = 0.0f;
+                if (t != 0)
+                {
+                    // the left neighbour lives in another warp: warm up over its last 12 samples (e^(-pi/2)^12 = 6.5e-9)
+                    const int rp = (int) ((a0 + n0 - 12) & (N - 1));
+                    #pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                    {
+                        const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[rp + 4 * q]);
+                        yin = fmaf (c2, yin, __fmul_rn (x4.x, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.y, c1g));
+                        yin = fmaf (c2, yin, __fmul_rn (x4.z, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.w, c1g));
+                    }
+                }
+            }
+            // e^(-pi/2 (j+1)): the filter constant is fixed by AudioFilter::m = 2 (RealTimeAudioAnalysis.h:127)
+            constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
+                                           8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,
+                                           3.132781128e-08f, 6.512412136e-09f };
+            #pragma unroll
+            for (int j = 0; j < 16; ++j)
+            {
+                if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
+                // Bartlett ramp at n = n0 + j: all 16 samples lie in the same half, the ramp values are exact in fp32
+                const float w = fmaf ((float) j, wseg_d, wseg_0);
+                workf[17 * t + j] = __fmul_rn (ys[j], w);                                         // phys (16 t + j)
+            }
+        }
+        __syncthreads();
+
+        // =========================== FFT-alpha: z = x w + i onepole (x) w ==============================
+        // Both windowed sequences are real: one complex transform carries B = FFT (x w) (spectral features) and
+        // C = FFT (filtered x w) (pitch), separated afterwards by conjugate symmetry.
         V16 io;
         {
-            // getRMSLevel squares in fp32 and sums in fp64; here the 16 squares of a thread are summed in fp32 first
-            // (two chains) and the 256 x 8 partials in fp64: 1e-7 relative on a feature compared at 1e-4
-            float sq0 = 0.0f, sq1 = 0.0f;
             const int rb = (int) ((a0 + t) & (N - 1));
             #pragma unroll
             for (int q = 0; q < Q1; ++q)
@@ -332,15 +403,12 @@ k_analyse (const AnalyseParams p)
                     // RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N; every term is a multiple
                     // of 2/N in [0, 1], so constant + t * 2/N is exact in fp32
                     const float w = (c < M) ? (float) c * (2.0f / N) + t2n : (1.0f - (float) (c - M) * (2.0f / N)) - t2n;
-                    io.v[q * R1 + n1] = make_float2 (x, __fmul_rn (x, w));
-                    if ((n1 & 1) == 0) sq0 = fmaf (x, x, sq0); else sq1 = fmaf (x, x, sq1);
+                    io.v[q * R1 + n1] = make_float2 (__fmul_rn (x, w), workf[phys (c + t)]);
                 }
-            double r1[1] = { (double) (sq0 + sq1) };
-            warp_sum<1> (r1);
-            if (lane == 0) sm.red[0][0][warp] = r1[0];
         }
+        __syncthreads();                                            // the work array is consumed: the exchange buffer is free
         io = fft_core<R1> (io, t);
-        __syncthreads();                                            // every stage-3 read is done: store X in natural order
+        __syncthreads();                                            // every stage-3 read is done: store Z in natural order
         {
             const int kl = klow<R1> (t);
             #pragma unroll
@@ -355,22 +423,33 @@ k_analyse (const AnalyseParams p)
             p0 = *reinterpret_cast<const float4*> (&prev_g[b0]);
             p1 = *reinterpret_cast<const float4*> (&prev_g[b0 + 4]);
         }
-        // split the packed spectrum: A = FFT (x), B = FFT (x w); keep Re A, Re B; Im B only for the slope quirk
+        // Split for this thread's own 8 consecutive bins k: Z[k] = B[k] + i C[k], conj Z[N-k] = B[k] - i C[k]
+        //   Re B = (Zk.x + Zn.x) / 2   Im B = (Zk.y - Zn.y) / 2   Re C = (Zk.y + Zn.y) / 2
+        // Re B stays in registers for the spectral passes; P[k] = Re C[k]^2 (PitchAnalyser.h:97-104, imaginary part
+        // cleared) goes to the P / Re A array as the imaginary input of FFT-beta.
+        float cr[8];
         float rawmax = 0.0f;     // SpectralCharacteristics.h:153: max |buf[j]|, j < M, over the interleaved Re/Im floats = bins k < M/2
-        #pragma unroll 4
-        for (int j = 0; j < 8; ++j)
+        float psum = 0.0f;       // sum of P^2 over the lower half: sets the power-of-two scale P is transformed at
         {
-            const int k = t + T * j;
-            const float2 zk = sm.ex[phys (k)];
-            const float2 zn = sm.ex[phys ((N - k) & (N - 1))];
-            const float reA = 0.5f * (zk.x + zn.x);
-            const float reB = 0.5f * (zk.y + zn.y);
-            const float imB = 0.5f * (zn.x - zk.x);
-            sm.specA[k] = reA;
-            sm.specB[k] = reB;
-            if (k < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
+            float pq[8];
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const int k = b0 + j;
+                const float2 zk = sm.ex[phys (k)];
+                const float2 zn = sm.ex[phys ((N - k) & (N - 1))];
+                const float reB = 0.5f * (zk.x + zn.x);
+                const float imB = 0.5f * (zk.y - zn.y);
+                const float reC = 0.5f * (zk.y + zn.y);
+                cr[j] = reB;
+                if (b0 < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
+                pq[j] = __fmul_rn (reC, reC);
+                psum = fmaf (pq[j], pq[j], psum);
+            }
+            *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (pq[0], pq[1], pq[2], pq[3]);
+            *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (pq[4], pq[5], pq[6], pq[7]);
+            if (t == 0) { const float cm = sm.ex[phys (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
         }
-        __syncthreads();
 
         // RMS (RealTimeAnalyser.h:207-208)
         double rms_sum = 0.0;
@@ -382,13 +461,9 @@ k_analyse (const AnalyseParams p)
         const double eps = 0.01 * (double) log_rms;                                               // SpectralCharacteristics.h:108
 
         // =========================== spectral features, pass 1 ========================================
-        float cr[8];
         ME lprod = me_one();
         int e_budget = 0;                // sum of |exponent| over this thread's gated bins: bounds how far its running product can move
         {
-            const float4 c0 = *reinterpret_cast<const float4*> (&sm.specB[b0]);
-            const float4 c1 = *reinterpret_cast<const float4*> (&sm.specB[b0 + 4]);
-            cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0;
             float maxre = 0.0f;
@@ -425,6 +500,7 @@ k_analyse (const AnalyseParams p)
             warp_sum<6> (s6);
             const float wmax = warp_maxf (maxre);
             const float wraw = warp_maxf (rawmax);
+            const float wps = warp_sumf (psum);
             const float wmar = ulps_to_margin (warp_minu (fgap));
             // inclusive warp scan of the extended-range product, in bin order
             ME inc = lprod;
@@ -445,13 +521,14 @@ k_analyse (const AnalyseParams p)
                 sm.fmaxs[warp] = wmax;
                 sm.fmins[0][warp] = wmar;
                 sm.fmins[1][warp] = wraw;
+                sm.psums[warp] = wps;
             }
         }
         __syncthreads();
         // every thread needs the magnitude sum, the centroid and the maxima; flux, the low-energy sum, the flatness sums
         // and the gate margin only go into the record and are combined by thread 0 when it writes it
         double mag_sum = 0.0, weighted = 0.0;
-        float rawmax_all = 0.0f, maxre_all = 0.0f;
+        float rawmax_all = 0.0f, maxre_all = 0.0f, psum_all = 0.0f;
         ME prefix = me_one();
         #pragma unroll
         for (int w = 0; w < NW; ++w)
@@ -459,7 +536,12 @@ k_analyse (const AnalyseParams p)
             mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w];
             maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
             rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
+            psum_all += sm.psums[w];
         }
+        // every read of the packed spectrum is behind the barrier above: the exchange buffer now takes this frame's Re B in
+        // bin order for the (rare, sequential) replay of the flatness product
+        *reinterpret_cast<float4*> (&specb[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);
+        *reinterpret_cast<float4*> (&specb[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
         #pragma unroll 1
         for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
@@ -495,7 +577,7 @@ k_analyse (const AnalyseParams p)
                 #pragma unroll 1
                 for (int j = 0; j < 8; ++j)
                 {
-                    const double re = (double) sm.specB[b0 + j];
+                    const double re = (double) specb[b0 + j];
                     const double mg = re * re;
                     if (mg > eps)
                     {
@@ -550,7 +632,7 @@ k_analyse (const AnalyseParams p)
                     #pragma unroll 1
                     for (; (b & 3) != 0; ++b)
                     {
-                        const double re = (double) sm.specB[b];
+                        const double re = (double) specb[b];
                         const double mg = re * re;
                         if (mg > eps) prod *= mg;
                     }
@@ -558,7 +640,7 @@ k_analyse (const AnalyseParams p)
                     #pragma unroll 1
                     for (; b < M && prod != 0.0 && ! isinf (prod); b += 4)
                     {
-                        const float4 v4 = *reinterpret_cast<const float4*> (&sm.specB[b]);
+                        const float4 v4 = *reinterpret_cast<const float4*> (&specb[b]);
                         const double m0 = (double) v4.x * (double) v4.x, m1 = (double) v4.y * (double) v4.y;
                         const double m2 = (double) v4.z * (double) v4.z, m3 = (double) v4.w * (double) v4.w;
                         if (m0 > eps) prod *= m0;
@@ -569,6 +651,12 @@ k_analyse (const AnalyseParams p)
                 }
                 sm.flat_prod = prod;
             }
+        }
+        if (t == 0)
+        {
+            // the part of the spectral record every thread already holds (the reductions follow after the next transform)
+            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->mean_e = mean_e; rec->max_e = max_e;
+            rec->centroid = centroid; rec->have_prev = have_prev ? 1.0f : 0.0f;
         }
         if (! silent)
         {
@@ -581,60 +669,38 @@ k_analyse (const AnalyseParams p)
             *reinterpret_cast<float4*> (&prev_g[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);       // :138 prev <- current
             *reinterpret_cast<float4*> (&prev_g[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
         }
+        if (! silent && ! have_prev) { have_prev = true; first_nonsilent = f; }
 
-        // =========================== one-pole filter + window -> work array ============================
-        // AudioFilter::filterAudio (RealTimeAudioAnalysis.h:106-125): y[0] = x[0]; y[n] = (pi/2) x[n] + e^(-pi/2) y[n-1].
-        // Each thread owns 16 consecutive samples: it runs the recurrence from a zero state over them, takes the state
-        // entering its segment from its left neighbour's zero-state end value (what that misses is e^(-pi/2)^16 = 1.2e-11
-        // of the state, far below fp32 resolution) and adds its decaying contribution e^(-pi/2)^(j+1) y_in.  FMAs and
-        // the folded gain differ from the reference's separate roundings by an ulp, well inside the rounding of the FFT
-        // this feeds.  The work array is free: the spectrum split was the last reader of the exchange buffer.
+
+        // =========================== FFT-beta: z = x + i 2^k P ==========================================
+        // A = FFT (x) feeds the harmonic features through its real part only, and the reference's inverse transform of
+        // the real, even sequence P (PitchAnalyser.h:120) is, up to 1/N, the real and even D = FFT (P).  Packed as
+        // Z = A + i D:  Re Z = Re A directly, and Im Z[s] + Im Z[N-s] = 2 D[s] because Im A is odd.  P is scaled by a
+        // power of two that matches its L2 norm to the frame's (an fp32 FFT's rounding noise is relative to the L2 norm
+        // of what it transforms): neither sequence's noise then rises above a small multiple of its own (the lag search is invariant to the scale, cnd = d^2 s / sum).
         {
-            const int n0 = 16 * t;
-            const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
-            const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
-            float ys[16];
-            #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            float pscale = 1.0f;
+            if (psum_all > 0.0f && psum_all < 3.0e38f && rms_sum > 0.0)
             {
-                const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
-                ys[4 * q] = x4.x; ys[4 * q + 1] = x4.y; ys[4 * q + 2] = x4.z; ys[4 * q + 3] = x4.w;
+                const int e_r = ((__double2hiint (rms_sum) >> 20) & 0x7ff) - 1023;                 // ||x||^2   ~ 2^e_r
+                const int e_p = (int) ((__float_as_uint (psum_all) >> 23) & 0xff) - 127;          // ||P||^2/2 ~ 2^e_p
+                int k2 = (e_r >> 1) - (e_p >> 1) + 1;                                             // ||2^k P|| = (1 .. 8) ||x||
+                k2 = max (-120, min (120, k2));
+                pscale = __int_as_float ((k2 + 127) << 23);
             }
-            float y = (t == 0) ? __fmul_rn (ys[0], gain) : __fmul_rn (ys[0], c1g);               // y[0] = x[0]
-            ys[0] = y;
+            const int rb = (int) ((a0 + t) & (N - 1));
             #pragma unroll
-            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (ys[j], c1g)); ys[j] = y; }
-            float yin = __shfl_up_sync (0xffffffffu, y, 1);
-            if (lane == 0)
-            {
-                yin = 0.0f;
-                if (t != 0)
+            for (int q = 0; q < Q1; ++q)
+                #pragma unroll
+                for (int n1 = 0; n1 < R1; ++n1)
                 {
-                    // the left neighbour lives in another warp: warm up over its last 12 samples (e^(-pi/2)^12 = 6.5e-9)
-                    const int rp = (int) ((a0 + n0 - 12) & (N - 1));
-                    #pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                    {
-                        const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[rp + 4 * q]);
-                        yin = fmaf (c2, yin, __fmul_rn (x4.x, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.y, c1g));
-                        yin = fmaf (c2, yin, __fmul_rn (x4.z, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.w, c1g));
-                    }
+                    const int c = n1 * 256 + T * q;
+                    const float x = __fmul_rn (sm.ring[(rb + c) & (N - 1)], gain);
+                    const int idx = (c < M) ? c + t : (N - c) - t;                                // P is even: P[N - n] = P[n]
+                    io.v[q * R1 + n1] = make_float2 (x, __fmul_rn (sm.pa[idx], pscale));
                 }
-            }
-            // e^(-pi/2 (j+1)): the filter constant is fixed by AudioFilter::m = 2 (RealTimeAudioAnalysis.h:127)
-            constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
-                                           8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,
-                                           3.132781128e-08f, 6.512412136e-09f };
-            #pragma unroll
-            for (int j = 0; j < 16; ++j)
-            {
-                if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
-                // Bartlett ramp at n = n0 + j: all 16 samples lie in the same half, the ramp values are exact in fp32
-                const float w = fmaf ((float) j, wseg_d, wseg_0);
-                workf[17 * t + j] = __fmul_rn (ys[j], w);                                         // phys (16 t + j)
-            }
         }
-        __syncthreads();                                            // ring is free: prefetch the next hop
+        __syncthreads();                                            // ring and exchange buffer are free: prefetch the next hop
         if (f + 1 < f_end)
         {
             const long jn = j_new + 1;
@@ -655,7 +721,15 @@ k_analyse (const AnalyseParams p)
                 if (t == 0) mbar_arrive (&sm.mbar);
             }
         }
-        // spectral record (flat_prod and the pass-3 partials were published by the barrier above)
+        io = fft_core<R1> (io, t);
+        __syncthreads();
+        {
+            const int kl = klow<R1> (t);
+            #pragma unroll
+            for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = io.v[s];
+        }
+        // spectral record (flat_prod and the pass-3 partials were published by the barrier before the transform; none of
+        // the slots read here is written again before the next frame's passes)
         if (t == 0)
         {
             // the pass-1 slots red[1][2..5], fmins[0] and the pass-2 slots red[0][1], red[0][3] are not reused before the next frame
@@ -678,43 +752,17 @@ k_analyse (const AnalyseParams p)
                 product = ldexp_normal (total.m, total.e); flat_state = 0.0f;
             }
             else { product = sm.flat_prod; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
-            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->flux = flux; rec->lhr = lhr;
+            rec->flux = flux; rec->lhr = lhr;
             rec->flat_sum = flat_sum; rec->count = count; rec->product = product; rec->var = var; rec->sie = sie;
-            rec->mean_e = mean_e; rec->evar = evar; rec->max_e = max_e;
-            rec->centroid = centroid; rec->flat_margin = flat_margin; rec->flat_state = silent ? 3.0f : flat_state;
-            rec->have_prev = have_prev ? 1.0f : 0.0f;
-        }
-        if (! silent && ! have_prev) { have_prev = true; first_nonsilent = f; }
-
-        // =========================== FFT2 (filtered, windowed) chained into FFT3 =======================
-        #pragma unroll
-        for (int q = 0; q < Q1; ++q)
-            #pragma unroll
-            for (int n1 = 0; n1 < R1; ++n1)
-                io.v[q * R1 + n1] = make_float2 (workf[phys (n1 * 256 + t + T * q)], 0.0f);
-        __syncthreads();
-        io = fft_core<R1> (io, t);
-        {
-            // PitchAnalyser::getComplexConjugateMultiplication (PitchAnalyser.h:97-104): Re^2, imaginary cleared
-            V16 c3 = io;
-            #pragma unroll
-            for (int s = 0; s < 16; ++s) c3.v[s] = make_float2 (__fmul_rn (c3.v[s].x, c3.v[s].x), 0.0f);
-            chain_permute<R1> (c3.v, io.v);
-        }
-        __syncthreads();
-        io = fft_core<R1> (io, klow<R1> (t));
-        __syncthreads();
-        {
-            // performRealOnlyInverseTransform scales by 1/N; only the real half d[0..N) can reach the lag search
-            const int kl = klow<R1> (t);
-            #pragma unroll
-            for (int s = 0; s < 16; ++s) workf[phys (kl + T * out_index<16> (s))] = __fmul_rn (io.v[s].x, 1.0f / N);
+            rec->evar = evar;
+            rec->flat_margin = flat_margin; rec->flat_state = silent ? 3.0f : flat_state;
         }
         __syncthreads();
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
         // workf holds d[s] (kept for the margins), workg receives cnd[s]; each thread owns s = 16 t .. 16 t + 15
         float av[16];                                                                             // ac[s] = d^2 s (PitchAnalyser.h:122-123)
+        float dv[16];
         double seg_exc;
         {
             const float s0f = (float) (16 * t);
@@ -722,9 +770,19 @@ k_analyse (const AnalyseParams p)
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                const float d = workf[17 * t + j];
+                const int s = 16 * t + j;
+                const float d = sm.ex[phys (s)].y + sm.ex[phys ((N - s) & (N - 1))].y;            // 2 * 2^k * D[s]
+                dv[j] = d;
                 av[j] = __fmul_rn (__fmul_rn (d, d), s0f + (float) j);                            // s = 0 contributes 0
                 runf += av[j];
+            }
+            // Re A of this thread's 8 bins moves to the P / Re A array (P was consumed by the transform)
+            {
+                float ra[8];
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) ra[j] = sm.ex[phys (b0 + j)].x;
+                *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (ra[0], ra[1], ra[2], ra[3]);
+                *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (ra[4], ra[5], ra[6], ra[7]);
             }
             double inc = (double) runf;
             #pragma unroll
@@ -736,11 +794,10 @@ k_analyse (const AnalyseParams p)
             seg_exc = __shfl_up_sync (0xffffffffu, inc, 1);
             if (lane == 0) seg_exc = 0.0;
             if (lane == 31) sm.pscan[warp] = inc;
-            if (t == 0) sm.d0 = workf[0];
+            if (t == 0) sm.d0 = dv[0];
         }
         __syncthreads();
         unsigned first_cross = 0xffffffffu, nd_mask = 0u;
-        float c_last;
         {
             double base = seg_exc;
             #pragma unroll
@@ -757,6 +814,7 @@ k_analyse (const AnalyseParams p)
                 float c = (sumf != 0.0f) ? __fmul_rn (av[j], rcp_approx (sumf)) : 0.0f;          // :146-154
                 if (j == 0 && t == 0) c = 1.0f;                                                   // :141
                 workg[17 * t + j] = c;
+                workf[17 * t + j] = dv[j];                                                        // every read of Z is behind the barrier above
                 if (j > 0 && ! (c < c_before)) nd_mask |= 1u << (j - 1);          // the descent (:178) stops at j - 1
                 c_before = c;
                 if (j >= 2 || t != 0)                                                             // the search starts at s = 2 (:169)
@@ -765,7 +823,7 @@ k_analyse (const AnalyseParams p)
                     if (c < best) { best = c; best_j = j; }                                       // :171-175 first strict minimum
                 }
             }
-            c_last = c_before;
+            sm.ndm[t] = (unsigned short) nd_mask;
             if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
             const unsigned best_s = best_j < 0 ? 0xffffffffu : (unsigned) (16 * t + best_j);
             const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | best_s;
@@ -773,21 +831,27 @@ k_analyse (const AnalyseParams p)
             const unsigned long long wkey = warp_minull (key);
             if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
         }
-        // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69)
-        float ar[8];
+        // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69).  The three
+        // neighbours the peak test needs from other threads (bins b0 - 2, b0 - 1, b0 + 8) are fetched now: after the next
+        // barrier every thread overwrites its own 8 bins of the array with the normalised magnitudes.
+        float ar[11];
         {
-            const float4 a0v = *reinterpret_cast<const float4*> (&sm.specA[b0]);
-            const float4 a1v = *reinterpret_cast<const float4*> (&sm.specA[b0 + 4]);
-            ar[0] = a0v.x; ar[1] = a0v.y; ar[2] = a0v.z; ar[3] = a0v.w; ar[4] = a1v.x; ar[5] = a1v.y; ar[6] = a1v.z; ar[7] = a1v.w;
+            const float4 a0v = *reinterpret_cast<const float4*> (&sm.pa[b0]);
+            const float4 a1v = *reinterpret_cast<const float4*> (&sm.pa[b0 + 4]);
+            ar[2] = a0v.x; ar[3] = a0v.y; ar[4] = a0v.z; ar[5] = a0v.w; ar[6] = a1v.x; ar[7] = a1v.y; ar[8] = a1v.z; ar[9] = a1v.w;
+            ar[0] = (b0 >= 2) ? sm.pa[b0 - 2] : 0.0f;
+            ar[1] = (b0 >= 1) ? sm.pa[b0 - 1] : 0.0f;
+            ar[10] = (b0 + 8 < M) ? sm.pa[b0 + 8] : 0.0f;
             double hsum = 0.0; float hmaxre = 0.0f;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { const double re = (double) ar[j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[j])); }
+            for (int j = 0; j < 8; ++j) { const double re = (double) ar[2 + j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[2 + j])); }
             double s1[1] = { hsum };
             warp_sum<1> (s1);
             const float wm = warp_maxf (hmaxre);
             if (lane == 0) { sm.red[0][4][warp] = s1[0]; sm.fmaxs[warp] = wm; }
         }
         __syncthreads();
+        // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
         unsigned s0 = 0xffffffffu;
         unsigned long long gkey = ~0ull;
         double hsum = 0.0; float hmaxre = 0.0f;
@@ -801,100 +865,77 @@ k_analyse (const AnalyseParams p)
         const double hmax = (double) hmaxre * (double) hmaxre;
         const bool crossed = (s0 != 0xffffffffu);
         const float e_abs = 1.0e-6f * fabsf (sm.d0);
+        int lag_i;                                                   // integer lag, -1 when the search found nothing (:165,188)
+        float pm = 1.0f;
+        if (crossed)
         {
-            // phase C: end of the descending run that starts at s0 (:178-181), margins of the threshold tests,
-            // runner-up of the global minimum (margin only).  Only the threads whose samples are involved do work.
-            unsigned send = 0xffffffffu;
-            float pm = 1.0f;
+            // end of the descending run that starts at s0 (:178-181): walk the per-segment "not descending" masks
+            int seg = (int) (s0 >> 4), j0 = (int) (s0 & 15u);
+            int s_end;
+            #pragma unroll 1
+            for (;;)
+            {
+                const unsigned m = ((unsigned) sm.ndm[seg]) >> j0;                      // positions j0 .. 14 of this segment
+                if (m != 0u) { s_end = 16 * seg + j0 + __ffs ((int) m) - 1; break; }
+                const int s = 16 * seg + 15;                                          // position 15 looks into the next segment
+                if (s + 1 >= N || ! (workg[phys (s + 1)] < workg[phys (s)])) { s_end = s; break; }
+                ++seg; j0 = 0;
+            }
+            // getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-203): the parabolic branch is unreachable
+            const int right = s_end + 1;
+            const float c_end = workg[phys (s_end)];
+            const float c_right = (right < N) ? workg[phys (right)] : 0.0f;          // cnd[N] = Im part of lag 0 = 0
+            lag_i = (c_end <= c_right) ? s_end : right;
+            // margins (diagnostics), spread over the whole CTA: the threshold tests s = 2 .. s0 (:176) ...
+            #pragma unroll 1
+            for (int s = 2 + t; s <= (int) s0; s += T)
+            {
+                const float c = workg[phys (s)];
+                pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[phys (s)], e_abs), 0.01f, 0.0f));
+            }
+            // ... and every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1
+            const int s_hi = min (s_end + 1, N - 1);
+            #pragma unroll 1
+            for (int s = (int) s0 + 1 + t; s <= s_hi; s += T)
+            {
+                const float c = workg[phys (s)], cp = workg[phys (s - 1)];
+                const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
+                const float up = cnd_uncertainty (cp, workf[phys (s - 1)], e_abs);
+                pm = fminf (pm, noisy_margin (c, u, cp, up));
+            }
+        }
+        else
+        {
+            const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
+            lag_i = (gidx == 0xffffffffu) ? -1 : (int) gidx;
+            // no crossing: every threshold test was false; runner-up of the global minimum for its margin
             float second = 100.0f;
-            const int seg0 = 16 * t;
-            if (crossed)
+            #pragma unroll 2
+            for (int j = (t == 0 ? 2 : 0); j < 16; ++j)
             {
-                if (seg0 + 15 >= (int) s0)
-                {
-                    const int j0 = max (0, (int) s0 - seg0);
-                    const unsigned m = nd_mask >> j0;                                  // positions j0 .. 14 of this segment
-                    if (m != 0u) send = (unsigned) (seg0 + j0 + __ffs ((int) m) - 1);
-                    else
-                    {
-                        const int s = seg0 + 15;                                        // position 15 looks into the next segment
-                        const bool has_next = (s + 1 < N);
-                        const float nxt = has_next ? workg[phys (s + 1)] : 0.0f;
-                        if (! (has_next && nxt < c_last)) send = (unsigned) s;
-                    }
-                }
-                if (seg0 <= (int) s0)
-                {
-                    #pragma unroll 1
-                    for (int j = (seg0 == 0 ? 2 : 0); j < 16 && seg0 + j <= (int) s0; ++j)
-                    {
-                        const float c = workg[17 * t + j];
-                        pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
-                    }
-                }
+                const float c = workg[17 * t + j];
+                pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
+                if (16 * t + j != (int) gidx) second = fminf (second, c);
             }
-            else
-            {
-                const int gidx = (int) (unsigned) (gkey & 0xffffffffull);
-                #pragma unroll 2
-                for (int j = (seg0 == 0 ? 2 : 0); j < 16; ++j)
-                {
-                    const float c = workg[17 * t + j];
-                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
-                    if (seg0 + j != gidx) second = fminf (second, c);
-                }
-            }
-            const unsigned wsend = warp_minu (send);
-            const float wpm = warp_minf (pm);
             const float wsec = warp_minf (second);
-            if (lane == 0) { sm.ucodes[0][warp] = wsend; sm.fmins[0][warp] = wpm; sm.fmins[1][warp] = wsec; }
+            if (lane == 0) sm.pmins[1][warp] = wsec;
         }
-        __syncthreads();
-        if (warp == 0)
         {
-            unsigned send = 0xffffffffu; float pm = 1.0f, second = 100.0f;
-            #pragma unroll
-            for (int w = 0; w < NW; ++w) { send = min (send, sm.ucodes[0][w]); pm = fminf (pm, sm.fmins[0][w]); second = fminf (second, sm.fmins[1][w]); }
-            float lag;
-            if (crossed)
-            {
-                // getInterpolatedValleyFromCumulativeDifferenceLagEstimate (:192-203): the parabolic branch is unreachable.
-                // The margins of every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1, one per lane.
-                const int s_end = (int) send;
-                const int s_hi = min (s_end + 1, N - 1);
-                #pragma unroll 1
-                for (int s = (int) s0 + 1 + lane; s <= s_hi; s += 32)
-                {
-                    const float c = workg[phys (s)], cp = workg[phys (s - 1)];
-                    const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
-                    const float up = cnd_uncertainty (cp, workf[phys (s - 1)], e_abs);
-                    pm = fminf (pm, noisy_margin (c, u, cp, up));
-                }
-                pm = warp_minf (pm);
-                const int right = s_end + 1;
-                const float c_end = workg[phys (s_end)];
-                const float c_right = (right < N) ? workg[phys (right)] : 0.0f;      // cnd[N] = Im part of lag 0 = 0
-                lag = (c_end <= c_right) ? (float) s_end : (float) right;
-            }
-            else
-            {
-                const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
-                lag = (gidx == 0xffffffffu) ? -1.0f : (float) gidx;                               // :165,188
-                pm = fminf (pm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
-            }
-            if (lane == 0)
-            {
-                sm.f0 = (nyquist * 2.0) / (double) lag;                                           // :57
-                rec->lag = lag; rec->pitch_margin = pm;
-            }
+            const float wpm = warp_minf (pm);
+            if (lane == 0) sm.pmins[0][warp] = wpm;
         }
-        __syncthreads();
+        // f0 = sample rate / lag and the bins derived from it come from tables built on the host with the reference's own
+        // double arithmetic (PitchAnalyser.h:57, HarmonicCharacteristics.h:158-185,246-249): slot 0 stands for lag -1
+        const int lag_slot = lag_i < 0 ? 0 : lag_i;
+        const double f0 = __ldg (&p.f0_tab[lag_slot]);
+        const short* htab = p.her_tab + (size_t) lag_slot * FX_HER_TAB_STRIDE;
+        const int f0_bin = (int) __ldg (&htab[18]);
+        int her_bin = -1;
+        if (warp == 0 && lane < 18) her_bin = (int) __ldg (&htab[lane]);       // consumed after the next barrier
 
         // =========================== harmonic features (HarmonicCharacteristics.h:46-106) =============
-        const double f0 = sm.f0;
         const bool hsilent = hsum < 0.005;                                                        // :88
         const double mean_mag = hsum * inv_m;                                                     // :86
-        const int f0_bin = (int) floor (f0 / frpb);                                               // :246-249
         {
             double sum_normed = 0.0, inharm = 0.0;
             unsigned pgap = 0xffffffffu, peak_mask = 0u;
@@ -902,11 +943,8 @@ k_analyse (const AnalyseParams p)
             const float mean_f = (float) mean_mag;
             // neighbours bin-2, bin-1, bin+1 (:136-143, loop end exclusive)
             double mgs[11];
-            mgs[0] = (b0 >= 2) ? (double) sm.specA[b0 - 2] * (double) sm.specA[b0 - 2] : 0.0;
-            mgs[1] = (b0 >= 1) ? (double) sm.specA[b0 - 1] * (double) sm.specA[b0 - 1] : 0.0;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) mgs[2 + j] = (double) ar[j] * (double) ar[j];
-            mgs[10] = (b0 + 8 < M) ? (double) sm.specA[b0 + 8] * (double) sm.specA[b0 + 8] : 0.0;
+            for (int j = 0; j < 11; ++j) mgs[j] = (double) ar[j] * (double) ar[j];
             float nm[8];
             #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -941,7 +979,7 @@ k_analyse (const AnalyseParams p)
                     peak_mask &= peak_mask - 1u;
                     const int bin = b0 + j;
                     if (bin == f0_bin) continue;                                                  // :220
-                    const double re = (double) sm.specA[bin];
+                    const double re = (double) sm.pa[bin];                                        // still Re A: this thread's own bins
                     const double mg = re * re;
                     double start_f = (double) bin * frpb;                                         // :223
                     if (start_f == 0.0) start_f = frpb * 0.5;
@@ -956,49 +994,52 @@ k_analyse (const AnalyseParams p)
                 }
             }
             const float pkm = ulps_to_margin (pgap);
-            *reinterpret_cast<float4*> (&workf[b0])     = make_float4 (nm[0], nm[1], nm[2], nm[3]);
-            *reinterpret_cast<float4*> (&workf[b0 + 4]) = make_float4 (nm[4], nm[5], nm[6], nm[7]);
+            // normalised magnitudes replace Re A in place (nobody reads another thread's Re A after the barrier above)
+            *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (nm[0], nm[1], nm[2], nm[3]);
+            *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (nm[4], nm[5], nm[6], nm[7]);
             double s3[3] = { sum_normed, inharm, npeaks };
             warp_sum<3> (s3);
             const float wpk = warp_minf (pkm);
             if (lane == 0) { sm.red[1][1][warp] = s3[0]; sm.red[1][2][warp] = s3[1]; sm.red[1][3][warp] = s3[2]; sm.fmins[0][warp] = wpk; }
         }
         __syncthreads();
+        // No barrier closes the frame: warp 0 finishes the harmonic record below while the other warps start the next
+        // frame's filter.  What it reads (the normalised magnitudes, the reduction slots) is not written again before the
+        // barriers of the next frame's first transform, which need warp 0.
         if (warp == 0)
         {
             // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
-            // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3; the sums are warp reductions
+            // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3 (bins from the table, -1 = not used: a sub-octave in
+            // f0's own bin is skipped (:163-164), harmonics stop at the first bin >= M (:174-175)); the sums are warp reductions
             double term = 0.0;
-            if (lane < 18 && ! hsilent)
+            if (her_bin >= 0 && ! hsilent)
             {
-                const double fr = (lane < 15) ? f0 * ldexp_normal (0.5, -lane) : f0 * (double) (lane - 14);
-                const int hb = (int) floor (fr / frpb);
-                // a sub-octave landing in f0's own bin is skipped (:163-164); harmonics stop at the first bin >= M (:174-175),
-                // and since they ascend, skipping every bin >= M is the same
-                const bool use = (lane < 15) ? (hb != f0_bin && hb >= 0 && hb < M) : (hb >= 0 && hb < M);
-                if (use)
-                {
-                    const int st = hb - 2 >= 0 ? hb - 2 : 0;
-                    const int en = hb + 2 < M ? hb + 2 : M;
-                    float mx = workf[hb];                                                         // :200-210
-                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, workf[bb]);
-                    term = (double) mx;
-                }
+                const int st = her_bin - 2 >= 0 ? her_bin - 2 : 0;
+                const int en = her_bin + 2 < M ? her_bin + 2 : M;
+                float mx = sm.pa[her_bin];                                                        // :200-210
+                for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, sm.pa[bb]);
+                term = (double) mx;
             }
             double s3[3] = { term, lane == 16 ? term : 0.0, (lane == 15 || lane == 17) ? term : 0.0 };
             warp_sum<3> (s3);
             if (lane == 0)
             {
-                double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f;
+                double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f, pmm = 1.0f, second = 100.0f;
                 #pragma unroll
-                for (int w = 0; w < NW; ++w) { sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += sm.red[1][3][w]; pkm = fminf (pkm, sm.fmins[0][w]); }
+                for (int w = 0; w < NW; ++w)
+                {
+                    sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += sm.red[1][3][w]; pkm = fminf (pkm, sm.fmins[0][w]);
+                    pmm = fminf (pmm, sm.pmins[0][w]); second = fminf (second, sm.pmins[1][w]);
+                }
+                if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
+                rec->lag = (float) lag_i; rec->pitch_margin = pmm;
                 rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
                 rec->score = s3[0]; rec->even = s3[1]; rec->odd = s3[2];
                 rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
             }
         }
-        __syncthreads();                                            // work array and reduction slots are reused by the next frame
     }
+    __syncthreads();                                                // the last frame's record and ring reads are complete
 
     // ---- chunk epilogue ----------------------------------------------------------------------------------
     if (t == 0) p.first_idx[track * p.n_chunks + chunk] = first_nonsilent;
@@ -1083,7 +1124,16 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         dg[FX_DIAG_NUM_PEAKS] = r.npeaks;
         dg[FX_DIAG_PEAK_MARGIN] = r.peak_margin;
         dg[FX_DIAG_FLAT_COUNT] = (float) r.count;
-        dg[FX_DIAG_FLAT_MARGIN] = r.flat_margin;
+        // The gate compares Re^2 with eps; Re carries the absolute rounding noise of an fp32 FFT (here and in the reference's
+        // own transform), taken as 1e-6 of the spectrum's rms like the pitch margin's floor.  For every bin the relative gap
+        // shrinks by at most 2 e / sqrt (eps) + e^2 / eps (|Re| >= sqrt (eps) above the gate, the gap is relative to eps below).
+        float fm = r.flat_margin;
+        if (eps > 0.0)
+        {
+            const double e_abs = 1.0e-6 * sqrt (r.mag_sum / (double) M);
+            fm = fmaxf (0.0f, fm - (float) (2.0 * e_abs / sqrt (eps) + e_abs * e_abs / eps));
+        }
+        dg[FX_DIAG_FLAT_MARGIN] = fm;
         dg[FX_DIAG_GATE_MARGIN] = gate_margin;
         dg[FX_DIAG_ONSET_MARGIN] = 1.0f;
         dg[FX_DIAG_FLAT_STATE] = r.flat_state;

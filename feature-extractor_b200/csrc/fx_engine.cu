@@ -37,6 +37,8 @@ struct fx_engine
     std::atomic<uint64_t> launches{0};
 
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
+    double *d_f0_tab = nullptr;
+    short  *d_her_tab = nullptr;
     double bin_var = 0.0;
     float  iir_c1 = 0.0f, iir_c2 = 0.0f;
 
@@ -127,6 +129,41 @@ void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2)
         }
 }
 
+// f0 and the harmonic bins as functions of the integer lag, in the reference's arithmetic (see AnalyseParams)
+void build_lag_tables (int N, double sample_rate, std::vector<double>& f0_tab, std::vector<short>& her_tab)
+{
+    const int M = N / 2;
+    const double nyquist = sample_rate / 2.0;
+    const double frpb = nyquist / (double) M;                       // HarmonicCharacteristics.h:53
+    f0_tab.assign ((size_t) N + 1, 0.0);
+    her_tab.assign ((size_t) (N + 1) * FX_HER_TAB_STRIDE, (short) -1);
+    auto clamp_short = [] (double v) { return (short) (v > 32767.0 ? 32767.0 : (v < -32768.0 ? -32768.0 : v)); };
+    for (int slot = 0; slot <= N; ++slot)
+    {
+        const double lag = slot == 0 ? -1.0 : (double) slot;
+        const double f0 = (nyquist * 2.0) / lag;                    // PitchAnalyser.h:57
+        f0_tab[(size_t) slot] = f0;
+        short* row = her_tab.data() + (size_t) slot * FX_HER_TAB_STRIDE;
+        const double f0_bin_d = floor (f0 / frpb);                  // :246-249
+        row[18] = clamp_short (f0_bin_d);
+        const int f0_bin = (int) f0_bin_d;
+        for (int l = 0; l < 15; ++l)
+        {
+            const double fr = f0 * ldexp (1.0, -(l + 1));           // f0 / 2^(l+1), exact scaling (:160-161)
+            const double hb = floor (fr / frpb);
+            // a sub-octave landing in f0's own bin is skipped (:163-164)
+            if (hb >= 0.0 && hb < (double) M && (int) hb != f0_bin) row[l] = (short) hb;
+        }
+        for (int h = 1; h <= 3; ++h)
+        {
+            const double fr = f0 * (double) h;                      // :171-172
+            const double hb = floor (fr / frpb);
+            // harmonics stop at the first bin >= M (:174-175); they ascend, so skipping every bin >= M is the same
+            if (hb >= 0.0 && hb < (double) M) row[14 + h] = (short) hb;
+        }
+    }
+}
+
 fx_status upload_params (fx_engine* e, cudaStream_t s)
 {
     if (! e->params_dirty) return FX_OK;
@@ -212,6 +249,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
     a.tw1 = e->d_tw1; a.tw2 = e->d_tw2;
+    a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab;
     a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
     const size_t coff = (size_t) t0 * (size_t) n_chunks;
@@ -259,7 +297,7 @@ void free_engine (fx_engine* e)
     if (! e) return;
     cudaSetDevice (e->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree (e->d_tw1); cudaFree (e->d_tw2);
+    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab);
     cudaFree (e->d_gain); cudaFree (e->d_mult); cudaFree (e->d_type); cudaFree (e->d_hist); cudaFree (e->d_reset);
     for (int i = 0; i < 2; ++i) { cudaFree (e->d_tail[i]); cudaFree (e->d_prev[i]); cudaFree (e->d_hrows[i]); }
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
@@ -348,6 +386,14 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
     FX_CREATE (cudaMalloc (&e->d_tw2, tw2.size() * sizeof (float2)));
     FX_CREATE (cudaMemcpy (e->d_tw1, tw1.data(), tw1.size() * sizeof (float2), cudaMemcpyHostToDevice));
     FX_CREATE (cudaMemcpy (e->d_tw2, tw2.data(), tw2.size() * sizeof (float2), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> f0_tab; std::vector<short> her_tab;
+        build_lag_tables (N, cfg->sample_rate, f0_tab, her_tab);
+        FX_CREATE (cudaMalloc (&e->d_f0_tab, f0_tab.size() * sizeof (double)));
+        FX_CREATE (cudaMalloc (&e->d_her_tab, her_tab.size() * sizeof (short)));
+        FX_CREATE (cudaMemcpy (e->d_f0_tab, f0_tab.data(), f0_tab.size() * sizeof (double), cudaMemcpyHostToDevice));
+        FX_CREATE (cudaMemcpy (e->d_her_tab, her_tab.data(), her_tab.size() * sizeof (short), cudaMemcpyHostToDevice));
+    }
 
     // SpectralCharacteristics.h:180-189: binVar accumulated sequentially in double
     {

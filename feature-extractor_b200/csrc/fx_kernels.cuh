@@ -9,6 +9,7 @@ namespace fx {
 
 constexpr int kHistRows   = 32;   // raw feature rows carried between calls (10-tap smoothing + <=16-deep onset window + 5)
 constexpr int kMaxOnsetHist = 16;
+#define FX_HER_TAB_STRIDE 20       // shorts per lag in AnalyseParams::her_tab
 
 // Per-frame sums K1 leaves for K1b (k_finalize).  fp64 wherever the reference accumulates in double.
 struct FrameRec
@@ -40,6 +41,12 @@ struct AnalyseParams
     float        iir_c1, iir_c2;   // pi/2 and exp (-pi/2) in fp32 (RealTimeAudioAnalysis.h:122)
     const float2* tw1;             // global twiddle tables (fx_fft.cuh layout)
     const float2* tw2;
+    // per-lag tables, slot lag = 1 .. window, slot 0 = "no lag found" (lag -1), evaluated on the host in the reference's own
+    // double arithmetic:  f0_tab[lag] = (nyquist * 2) / lag  (PitchAnalyser.h:57)
+    // her_tab[lag][0..14] = bin of the sub-octave f0 / 2^(l+1), [15..17] = bin of the harmonic h f0, h = 1..3, or -1 when the
+    // reference does not use it (HarmonicCharacteristics.h:158-185); [18] = bin of f0 itself (:246-249), clamped to a short
+    const double* f0_tab;
+    const short*  her_tab;
     // outputs
     FrameRec*    rec;              // [n_tracks][n_frames]
     float*       first_spec;       // [n_tracks][n_chunks][M]  Re spectrum (windowed path) of the chunk's first non-silent frame
