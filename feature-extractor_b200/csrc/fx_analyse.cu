@@ -145,11 +145,34 @@ template <int K> __device__ __forceinline__ void warp_sum (double (&v)[K])
         #pragma unroll
         for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync (0xffffffffu, v[k], off);
 }
-__device__ __forceinline__ double warp_max (double v)
+// Sum K (a power of two <= 8) doubles over the warp with a transposed butterfly: each of the first log2 K steps halves the
+// number of values a lane carries (it keeps one half of the pairs and sends the other half to its partner), the remaining
+// steps are plain butterflies on one value: K - 1 + (5 - log2 K) exchanges instead of 5 K.  Afterwards v[0] of every lane
+// holds the warp total of value warp_sum_slot<K> (lane).
+template <int K> __device__ __forceinline__ int warp_sum_slot (int lane)
 {
+    int idx = 0;
     #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmax (v, __shfl_xor_sync (0xffffffffu, v, off));
-    return v;
+    for (int b = 0; (K >> (b + 1)) > 0; ++b) idx += ((lane >> b) & 1) * (K >> (b + 1));
+    return idx;
+}
+template <int K> __device__ __forceinline__ void warp_sum_t (double (&v)[K], int lane)
+{
+    int b = 0;
+    #pragma unroll
+    for (int half = K / 2; half > 0; half >>= 1, ++b)
+    {
+        const bool up = (lane >> b) & 1;
+        #pragma unroll
+        for (int i = 0; i < half; ++i)
+        {
+            const double keep = up ? v[i + half] : v[i];
+            const double send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync (0xffffffffu, send, 1 << b);
+        }
+    }
+    #pragma unroll
+    for (int off = K; off < 32; off <<= 1) v[0] += __shfl_xor_sync (0xffffffffu, v[0], off);
 }
 __device__ __forceinline__ float warp_sumf (float v)
 {
@@ -157,30 +180,12 @@ __device__ __forceinline__ float warp_sumf (float v)
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync (0xffffffffu, v, off);
     return v;
 }
-__device__ __forceinline__ float warp_minf (float v)
-{
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fminf (v, __shfl_xor_sync (0xffffffffu, v, off));
-    return v;
-}
-__device__ __forceinline__ float warp_maxf (float v)
-{
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmaxf (v, __shfl_xor_sync (0xffffffffu, v, off));
-    return v;
-}
-__device__ __forceinline__ unsigned warp_minu (unsigned v)
-{
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = min (v, __shfl_xor_sync (0xffffffffu, v, off));
-    return v;
-}
-__device__ __forceinline__ unsigned long long warp_minull (unsigned long long v)
-{
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { const unsigned long long o = __shfl_xor_sync (0xffffffffu, v, off); v = o < v ? o : v; }
-    return v;
-}
+// Single-instruction warp reductions (REDUX) on integers; non-negative floats order like their bit patterns, so the
+// maxima of |Re| and the minima of the (non-negative) margins go through the same instruction.
+__device__ __forceinline__ unsigned warp_minu (unsigned v) { return __reduce_min_sync (0xffffffffu, v); }
+__device__ __forceinline__ int warp_addi (int v) { return __reduce_add_sync (0xffffffffu, v); }
+__device__ __forceinline__ float warp_max_nonneg (float v) { return __uint_as_float (__reduce_max_sync (0xffffffffu, __float_as_uint (v))); }
+__device__ __forceinline__ float warp_min_nonneg (float v) { return __uint_as_float (__reduce_min_sync (0xffffffffu, __float_as_uint (v))); }
 
 // ---------------------------------------------------------------------------------------------------------
 template <int R1> struct Smem
@@ -195,6 +200,8 @@ template <int R1> struct Smem
     float    ring[N];                // ring[a & (N-1)] = absolute sample a of the track
     float    pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
     double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
+    int      icount[NW];             // flatness gate count, warp totals
+    int      ipeaks[NW];             // number of spectral peaks, warp totals
     double   scan_m[NW];             // flatness product scan, warp totals
     int      scan_e[NW];
     double   pscan[NW];              // pitch cumulative sum scan, warp totals
@@ -205,7 +212,7 @@ template <int R1> struct Smem
     float    psums[NW];
     float    pmins[2][NW];           // pitch margin / runner-up partials
     unsigned short ndm[T];           // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178)
-    double   flat_prod;
+    double   ev_prod[NW];           // flatness product replayed by the warp's earliest range event
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     uint64_t mbar;
 };
@@ -241,7 +248,6 @@ k_analyse (const AnalyseParams p)
     S& sm = *reinterpret_cast<S*> (fx_smem_raw);
     float* workf = reinterpret_cast<float*> (sm.ex);          // fp32 view, skewed index phys (n)
     float* workg = workf + D::EX_LEN;                          // second fp32 array in the same buffer
-    float* specb = workf;                                      // Re B in bin order (unskewed) while the spectral passes run
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long cta = blockIdx.x;
@@ -309,7 +315,6 @@ k_analyse (const AnalyseParams p)
     const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
     const int b0 = 8 * t;                                           // this thread's 8 consecutive bins
     const double inv_m = 1.0 / (double) M;                          // exact: M is a power of two
-    const float t2n = (float) t * (2.0f / N);                       // window ramp at this thread's offset (exact)
     // the same ramp over this thread's 16 consecutive samples (filter / pitch layout): w = wseg_0 + j wseg_d
     const float wseg_0 = (16 * t < M) ? (float) (16 * t) * (2.0f / N) : 1.0f - (float) (16 * t - M) * (2.0f / N);
     const float wseg_d = (16 * t < M) ? (2.0f / N) : -(2.0f / N);
@@ -337,13 +342,13 @@ k_analyse (const AnalyseParams p)
             const int n0 = 16 * t;
             const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
             const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
-            float ys[16];
+            float xs[16], ys[16];
             float sq0 = 0.0f, sq1 = 0.0f;
             #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
                 const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
-                ys[4 * q] = x4.x; ys[4 * q + 1] = x4.y; ys[4 * q + 2] = x4.z; ys[4 * q + 3] = x4.w;
+                xs[4 * q] = x4.x; xs[4 * q + 1] = x4.y; xs[4 * q + 2] = x4.z; xs[4 * q + 3] = x4.w;
                 sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
             }
             {
@@ -351,10 +356,10 @@ k_analyse (const AnalyseParams p)
                 warp_sum<1> (r1);
                 if (lane == 0) sm.red[0][0][warp] = r1[0];
             }
-            float y = (t == 0) ? __fmul_rn (ys[0], gain) : __fmul_rn (ys[0], c1g);               // y[0] = x[0]
+            float y = (t == 0) ? __fmul_rn (xs[0], gain) : __fmul_rn (xs[0], c1g);               // y[0] = x[0]
             ys[0] = y;
             #pragma unroll
-            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (ys[j], c1g)); ys[j] = y; }
+            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (xs[j], c1g)); ys[j] = y; }
             float yin = __shfl_up_sync (0xffffffffu, y, 1);
             if (lane == 0)
             {
@@ -376,13 +381,16 @@ k_analyse (const AnalyseParams p)
             constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
                                            8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,
                                            3.132781128e-08f, 6.512412136e-09f };
+            // Both windowed sequences go to the exchange buffer in natural (skewed) order as the packed input of FFT-alpha,
+            // z[n] = x[n] w[n] + i y[n] w[n]: the transform's strided gather is then one 8-byte load per point.
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
                 if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
-                // Bartlett ramp at n = n0 + j: all 16 samples lie in the same half, the ramp values are exact in fp32
+                // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
+                // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
                 const float w = fmaf ((float) j, wseg_d, wseg_0);
-                workf[17 * t + j] = __fmul_rn (ys[j], w);                                         // phys (16 t + j)
+                sm.ex[17 * t + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));   // phys (16 t + j)
             }
         }
         __syncthreads();
@@ -391,22 +399,13 @@ k_analyse (const AnalyseParams p)
         // Both windowed sequences are real: one complex transform carries B = FFT (x w) (spectral features) and
         // C = FFT (filtered x w) (pitch), separated afterwards by conjugate symmetry.
         V16 io;
-        {
-            const int rb = (int) ((a0 + t) & (N - 1));
+        #pragma unroll
+        for (int q = 0; q < Q1; ++q)
             #pragma unroll
-            for (int q = 0; q < Q1; ++q)
-                #pragma unroll
-                for (int n1 = 0; n1 < R1; ++n1)
-                {
-                    const int c = n1 * 256 + T * q;                                               // n = c + t, c a multiple of T
-                    const float x = __fmul_rn (sm.ring[(rb + c) & (N - 1)], gain);                // AudioDataCollector.h:88
-                    // RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N; every term is a multiple
-                    // of 2/N in [0, 1], so constant + t * 2/N is exact in fp32
-                    const float w = (c < M) ? (float) c * (2.0f / N) + t2n : (1.0f - (float) (c - M) * (2.0f / N)) - t2n;
-                    io.v[q * R1 + n1] = make_float2 (__fmul_rn (x, w), workf[phys (c + t)]);
-                }
-        }
-        __syncthreads();                                            // the work array is consumed: the exchange buffer is free
+            for (int n1 = 0; n1 < R1; ++n1)
+                io.v[q * R1 + n1] = sm.ex[phys (n1 * 256 + T * q + t)];
+        // no barrier: stage 1 is in place per thread (it stores to ex[k1 * ROW + phys (m)], exactly the 16 slots
+        // ex[phys (n1 * 256 + m)] = ex[n1 * ROW + phys (m)] this thread has just read)
         io = fft_core<R1> (io, t);
         __syncthreads();                                            // every stage-3 read is done: store Z in natural order
         {
@@ -462,10 +461,12 @@ k_analyse (const AnalyseParams p)
 
         // =========================== spectral features, pass 1 ========================================
         ME lprod = me_one();
+        double flat_sum_thread = 0.0;
         int e_budget = 0;                // sum of |exponent| over this thread's gated bins: bounds how far its running product can move
         {
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
-            double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0;
+            double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0;
+            int count = 0;
             float maxre = 0.0f;
             unsigned fgap = 0xffffffffu;
             const float eps_f = (float) eps;
@@ -484,7 +485,7 @@ k_analyse (const AnalyseParams p)
                 if (mg > eps)                                                                    // :89-94
                 {
                     flat_sum += mg;
-                    count += 1.0;
+                    count += 1;
                     const ME q = me_from (mg);
                     mprod *= q.m;                                                                // >= 2^-8: no renormalisation needed
                     esum += q.e;
@@ -496,10 +497,12 @@ k_analyse (const AnalyseParams p)
                 maxre = fmaxf (maxre, fabsf (cr[j]));
             }
             lprod = me_from (mprod); lprod.e += esum;
-            double s6[6] = { mag_sum, weighted, flux, lhr, flat_sum, count };
-            warp_sum<6> (s6);
-            const float wmax = warp_maxf (maxre);
-            const float wraw = warp_maxf (rawmax);
+            double s4[4] = { mag_sum, weighted, flux, lhr };
+            warp_sum_t<4> (s4, lane);
+            flat_sum_thread = flat_sum;                                                           // summed with the pass-2 values
+            const int wcount = warp_addi (count);
+            const float wmax = warp_max_nonneg (maxre);
+            const float wraw = warp_max_nonneg (rawmax);
             const float wps = warp_sumf (psum);
             const float wmar = ulps_to_margin (warp_minu (fgap));
             // inclusive warp scan of the extended-range product, in bin order
@@ -514,10 +517,10 @@ k_analyse (const AnalyseParams p)
             if (lane == 0) exc = me_one();
             lprod = exc;                                                                         // lane-exclusive prefix within the warp
             if (lane == 31) { sm.scan_m[warp] = inc.m; sm.scan_e[warp] = inc.e; }
+            if (lane < 4) sm.red[1][warp_sum_slot<4> (lane)][warp] = s4[0];
             if (lane == 0)
             {
-                #pragma unroll
-                for (int k = 0; k < 6; ++k) sm.red[1][k][warp] = s6[k];
+                sm.icount[warp] = wcount;
                 sm.fmaxs[warp] = wmax;
                 sm.fmins[0][warp] = wmar;
                 sm.fmins[1][warp] = wraw;
@@ -538,10 +541,6 @@ k_analyse (const AnalyseParams p)
             rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
             psum_all += sm.psums[w];
         }
-        // every read of the packed spectrum is behind the barrier above: the exchange buffer now takes this frame's Re B in
-        // bin order for the (rare, sequential) replay of the flatness product
-        *reinterpret_cast<float4*> (&specb[b0])     = make_float4 (cr[0], cr[1], cr[2], cr[3]);
-        *reinterpret_cast<float4*> (&specb[b0 + 4]) = make_float4 (cr[4], cr[5], cr[6], cr[7]);
         #pragma unroll 1
         for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
@@ -551,11 +550,19 @@ k_analyse (const AnalyseParams p)
         const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
         const double inv_max_e = 1.0 / max_e;
 
-        // =========================== pass 2: spread, slope sums, flatness range events ================
-        unsigned ev_code = 0xffffffffu;
-        ME ev_run = me_one();
+        // =========================== pass 2: spread, slope sums, energy variance, flatness range events ===
+        // :177 meanE = (sum of mag / maxE) / M.  The reference's third pass (:182-190, deviations from meanE) runs inside
+        // this one because the mean follows from pass 1's magnitude sum: sum (mag * (1 / maxE)) and magSum * (1 / maxE)
+        // differ by fp64 rounding only (1e-16 relative on a feature compared at 1e-4).
+        const double mean_e = (mag_sum * inv_max_e) * inv_m;
+        // Re B[k] recomputed from the packed spectrum, which stays in the exchange buffer until FFT-beta's barrier
+        // (same expression as the split: bit-identical); only the rare sequential paths below use it
+        auto reb_at = [&] (int k) -> double
         {
-            double var = 0.0, se = 0.0, sie = 0.0;
+            return (double) (0.5f * (sm.ex[phys (k)].x + sm.ex[phys ((N - k) & (N - 1))].x));
+        };
+        {
+            double var = 0.0, sie = 0.0, evar = 0.0;
             const double cn = (double) centroid / nyquist;                                        // :137
             #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -565,19 +572,25 @@ k_analyse (const AnalyseParams p)
                 const double dv = ((double) bin + 0.5) * inv_m - cn;                              // fc / nyquist = (bin + 1/2) / M
                 var += (dv * dv) * mg;
                 const double e = mg * inv_max_e;                                                  // :172
-                se += e;
                 sie += (double) bin * e;                                                          // :175
+                const double de = e - mean_e;                                                     // :182-190
+                evar += de * de;
             }
             // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is
-            // still in range and the exponent budget of its bins reaches a limit; a prefix already out of range
-            // means an earlier thread owns the first event.
+            // still in range and the exponent budget of its bins reaches a limit.  Every thread that sees such an event
+            // replays the reference's sequential IEEE multiply (gradual underflow included, :92) from its event bin; the
+            // earliest event of the CTA (smallest code) is the one the reference's running product meets first, and
+            // thread 0 picks that thread's product when it writes the record.  Later events are speculative work that
+            // only arises when the extended-range product wanders back into range (rare).
+            unsigned ev_code = 0xffffffffu;
+            double ev_prod = 0.0;
             if (prefix.e < 1025 && prefix.e > -1022 && (prefix.e + e_budget >= 1025 || prefix.e - e_budget <= -1022))
             {
                 ME run = prefix;
                 #pragma unroll 1
                 for (int j = 0; j < 8; ++j)
                 {
-                    const double re = (double) specb[b0 + j];
+                    const double re = reb_at (b0 + j);
                     const double mg = re * re;
                     if (mg > eps)
                     {
@@ -585,72 +598,46 @@ k_analyse (const AnalyseParams p)
                         if (nxt.e >= 1025 || nxt.e <= -1022)
                         {
                             ev_code = (unsigned) (b0 + j) * 2u + (nxt.e >= 1025 ? 1u : 0u);
-                            ev_run = run;
                             break;
                         }
                         run = nxt;
                     }
                 }
-            }
-            double s3[3] = { var, se, sie };
-            warp_sum<3> (s3);
-            const unsigned wev = warp_minu (ev_code);
-            if (lane == 0)
-            {
-                sm.red[0][1][warp] = s3[0]; sm.red[0][2][warp] = s3[1]; sm.red[0][3][warp] = s3[2];
-                sm.ucodes[0][warp] = wev;
-            }
-        }
-        __syncthreads();
-        double se = 0.0;
-        unsigned ev = 0xffffffffu;
-        #pragma unroll
-        for (int w = 0; w < NW; ++w)
-        {
-            se += sm.red[0][2][w];
-            ev = min (ev, sm.ucodes[0][w]);
-        }
-        const double mean_e = se * inv_m;                                                         // :177
-        {
-            // pass 3: energy variance (:182-190)
-            double evar = 0.0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) { const double d = (double) cr[j] * (double) cr[j] * inv_max_e - mean_e; evar += d * d; }
-            double s1[1] = { evar };
-            warp_sum<1> (s1);
-            if (lane == 0) sm.red[1][0][warp] = s1[0];
-            // flatness product left the normal fp64 range at bin ev >> 1: the owner of that bin replays the
-            // reference's sequential IEEE multiply (gradual underflow included) from there (:92)
-            if (ev != 0xffffffffu && ev == ev_code)
-            {
-                double prod;
-                if (ev & 1u) prod = INFINITY;
-                else
+                if (ev_code != 0xffffffffu)
                 {
-                    prod = ldexp_normal (ev_run.m, ev_run.e);
-                    int b = (int) (ev >> 1);
-                    #pragma unroll 1
-                    for (; (b & 3) != 0; ++b)
+                    if (ev_code & 1u) ev_prod = INFINITY;
+                    else
                     {
-                        const double re = (double) specb[b];
-                        const double mg = re * re;
-                        if (mg > eps) prod *= mg;
-                    }
-                    // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group
-                    #pragma unroll 1
-                    for (; b < M && prod != 0.0 && ! isinf (prod); b += 4)
-                    {
-                        const float4 v4 = *reinterpret_cast<const float4*> (&specb[b]);
-                        const double m0 = (double) v4.x * (double) v4.x, m1 = (double) v4.y * (double) v4.y;
-                        const double m2 = (double) v4.z * (double) v4.z, m3 = (double) v4.w * (double) v4.w;
-                        if (m0 > eps) prod *= m0;
-                        if (m1 > eps) prod *= m1;
-                        if (m2 > eps) prod *= m2;
-                        if (m3 > eps) prod *= m3;
+                        ev_prod = ldexp_normal (run.m, run.e);
+                        int b = (int) (ev_code >> 1);
+                        #pragma unroll 1
+                        for (; (b & 3) != 0; ++b)
+                        {
+                            const double re = reb_at (b);
+                            const double mg = re * re;
+                            if (mg > eps) ev_prod *= mg;
+                        }
+                        // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group
+                        #pragma unroll 1
+                        for (; b < M && ev_prod != 0.0 && ! isinf (ev_prod); b += 4)
+                        {
+                            #pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const double re = reb_at (b + u);
+                                const double mg = re * re;
+                                if (mg > eps) ev_prod *= mg;
+                            }
+                        }
                     }
                 }
-                sm.flat_prod = prod;
             }
+            double s4[4] = { var, sie, flat_sum_thread, evar };
+            warp_sum_t<4> (s4, lane);
+            const unsigned wev = warp_minu (ev_code);
+            if (lane < 4) sm.red[0][1 + warp_sum_slot<4> (lane)][warp] = s4[0];                   // slots 1..4: var, sie, flat_sum, evar
+            if (lane == 0) sm.ucodes[0][warp] = wev;
+            if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // codes are unique: one lane
         }
         if (t == 0)
         {
@@ -728,20 +715,21 @@ k_analyse (const AnalyseParams p)
             #pragma unroll
             for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = io.v[s];
         }
-        // spectral record (flat_prod and the pass-3 partials were published by the barrier before the transform; none of
+        // spectral record (the pass-2 partials and replayed products were published by the barrier before the transform; none of
         // the slots read here is written again before the next frame's passes)
         if (t == 0)
         {
-            // the pass-1 slots red[1][2..5], fmins[0] and the pass-2 slots red[0][1], red[0][3] are not reused before the next frame
+            // the pass-1 slots red[1][2..3], icount, fmins[0] and the pass-2 slots red[0][1..4], ucodes[0], ev_prod are not written again before the barrier below
             double evar = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, var = 0.0, sie = 0.0;
             float flat_margin = 1.0f;
+            unsigned ev = 0xffffffffu; int ev_warp = 0;
             #pragma unroll
             for (int w = 0; w < NW; ++w)
             {
-                evar += sm.red[1][0][w];
-                flux += sm.red[1][2][w]; lhr += sm.red[1][3][w]; flat_sum += sm.red[1][4][w]; count += sm.red[1][5][w];
-                var += sm.red[0][1][w]; sie += sm.red[0][3][w];
+                flux += sm.red[1][2][w]; lhr += sm.red[1][3][w]; count += (double) sm.icount[w];
+                var += sm.red[0][1][w]; sie += sm.red[0][2][w]; flat_sum += sm.red[0][3][w]; evar += sm.red[0][4][w];
                 flat_margin = fminf (flat_margin, sm.fmins[0][w]);
+                if (sm.ucodes[0][w] < ev) { ev = sm.ucodes[0][w]; ev_warp = w; }
             }
             double product; float flat_state;
             if (ev == 0xffffffffu)
@@ -751,7 +739,7 @@ k_analyse (const AnalyseParams p)
                 for (int w = 0; w < NW; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; total = me_mul (total, wt); }
                 product = ldexp_normal (total.m, total.e); flat_state = 0.0f;
             }
-            else { product = sm.flat_prod; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
+            else { product = sm.ev_prod[ev_warp]; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
             rec->flux = flux; rec->lhr = lhr;
             rec->flat_sum = flat_sum; rec->count = count; rec->product = product; rec->var = var; rec->sie = sie;
             rec->evar = evar;
@@ -826,9 +814,11 @@ k_analyse (const AnalyseParams p)
             sm.ndm[t] = (unsigned short) nd_mask;
             if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
             const unsigned best_s = best_j < 0 ? 0xffffffffu : (unsigned) (16 * t + best_j);
-            const unsigned long long key = ((unsigned long long) __float_as_uint (best) << 32) | best_s;
+            // first strict minimum of the warp: smallest value (cnd >= 0 orders like its bit pattern), then smallest index
             const unsigned wfc = warp_minu (first_cross);
-            const unsigned long long wkey = warp_minull (key);
+            const unsigned wbest = warp_minu (__float_as_uint (best));
+            const unsigned widx = warp_minu (__float_as_uint (best) == wbest ? best_s : 0xffffffffu);
+            const unsigned long long wkey = ((unsigned long long) wbest << 32) | widx;
             if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
         }
         // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69).  The three
@@ -847,8 +837,8 @@ k_analyse (const AnalyseParams p)
             for (int j = 0; j < 8; ++j) { const double re = (double) ar[2 + j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[2 + j])); }
             double s1[1] = { hsum };
             warp_sum<1> (s1);
-            const float wm = warp_maxf (hmaxre);
-            if (lane == 0) { sm.red[0][4][warp] = s1[0]; sm.fmaxs[warp] = wm; }
+            const float wm = warp_max_nonneg (hmaxre);
+            if (lane == 0) { sm.red[0][5][warp] = s1[0]; sm.fmaxs[warp] = wm; }
         }
         __syncthreads();
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
@@ -860,7 +850,7 @@ k_analyse (const AnalyseParams p)
         {
             s0 = min (s0, sm.ucodes[1][w]);
             gkey = sm.keys[w] < gkey ? sm.keys[w] : gkey;
-            hsum += sm.red[0][4][w]; hmaxre = fmaxf (hmaxre, sm.fmaxs[w]);
+            hsum += sm.red[0][5][w]; hmaxre = fmaxf (hmaxre, sm.fmaxs[w]);
         }
         const double hmax = (double) hmaxre * (double) hmaxre;
         const bool crossed = (s0 != 0xffffffffu);
@@ -917,11 +907,11 @@ k_analyse (const AnalyseParams p)
                 pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
                 if (16 * t + j != (int) gidx) second = fminf (second, c);
             }
-            const float wsec = warp_minf (second);
+            const float wsec = warp_min_nonneg (second);
             if (lane == 0) sm.pmins[1][warp] = wsec;
         }
         {
-            const float wpm = warp_minf (pm);
+            const float wpm = warp_min_nonneg (pm);
             if (lane == 0) sm.pmins[0][warp] = wpm;
         }
         // f0 = sample rate / lag and the bins derived from it come from tables built on the host with the reference's own
@@ -968,7 +958,7 @@ k_analyse (const AnalyseParams p)
                     if (peak) peak_mask |= 1u << j;
                 }
             }
-            const double npeaks = (double) __popc (peak_mask);
+            const int npeaks = __popc (peak_mask);
             // calculateInharmonicity (:212-244) over this thread's peaks
             if (f0 > 0.0)                                                                         // :98
             {
@@ -997,10 +987,12 @@ k_analyse (const AnalyseParams p)
             // normalised magnitudes replace Re A in place (nobody reads another thread's Re A after the barrier above)
             *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (nm[0], nm[1], nm[2], nm[3]);
             *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (nm[4], nm[5], nm[6], nm[7]);
-            double s3[3] = { sum_normed, inharm, npeaks };
-            warp_sum<3> (s3);
-            const float wpk = warp_minf (pkm);
-            if (lane == 0) { sm.red[1][1][warp] = s3[0]; sm.red[1][2][warp] = s3[1]; sm.red[1][3][warp] = s3[2]; sm.fmins[0][warp] = wpk; }
+            double s2[2] = { sum_normed, inharm };
+            warp_sum_t<2> (s2, lane);
+            const int wnp = warp_addi (npeaks);
+            const float wpk = warp_min_nonneg (pkm);
+            if (lane < 2) sm.red[1][1 + warp_sum_slot<2> (lane)][warp] = s2[0];
+            if (lane == 0) { sm.ipeaks[warp] = wnp; sm.fmins[0][warp] = wpk; }
         }
         __syncthreads();
         // No barrier closes the frame: warp 0 finishes the harmonic record below while the other warps start the next
@@ -1020,21 +1012,24 @@ k_analyse (const AnalyseParams p)
                 for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, sm.pa[bb]);
                 term = (double) mx;
             }
-            double s3[3] = { term, lane == 16 ? term : 0.0, (lane == 15 || lane == 17) ? term : 0.0 };
-            warp_sum<3> (s3);
+            // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
+            const double even = __shfl_sync (0xffffffffu, term, 16);
+            const double odd = __shfl_sync (0xffffffffu, term, 15) + __shfl_sync (0xffffffffu, term, 17);
+            double s1[1] = { term };
+            warp_sum<1> (s1);
             if (lane == 0)
             {
                 double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f, pmm = 1.0f, second = 100.0f;
                 #pragma unroll
                 for (int w = 0; w < NW; ++w)
                 {
-                    sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += sm.red[1][3][w]; pkm = fminf (pkm, sm.fmins[0][w]);
+                    sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += (double) sm.ipeaks[w]; pkm = fminf (pkm, sm.fmins[0][w]);
                     pmm = fminf (pmm, sm.pmins[0][w]); second = fminf (second, sm.pmins[1][w]);
                 }
                 if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
                 rec->lag = (float) lag_i; rec->pitch_margin = pmm;
                 rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
-                rec->score = s3[0]; rec->even = s3[1]; rec->odd = s3[2];
+                rec->score = s1[0]; rec->even = even; rec->odd = odd;
                 rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
             }
         }
