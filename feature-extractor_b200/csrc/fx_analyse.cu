@@ -462,14 +462,17 @@ k_analyse (const AnalyseParams p)
         // =========================== spectral features, pass 1 ========================================
         ME lprod = me_one();
         double flat_sum_thread = 0.0;
-        int e_budget = 0;                // sum of |exponent| over this thread's gated bins: bounds how far its running product can move
         {
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0;
             int count = 0;
             float maxre = 0.0f;
-            unsigned fgap = 0xffffffffu;
+            // gate margin: the smallest distance of |Re| from sqrt (eps), relative to sqrt (eps) -- a lower bound of the
+            // relative gap between Re^2 and eps ((1 + d)^2 - 1 >= d and 1 - (1 - d)^2 >= d), two instructions per bin
             const float eps_f = (float) eps;
+            const float gate_s = __fsqrt_rn (eps_f);
+            const float gate_inv = gate_s > 0.0f ? __fdividef (1.0f, gate_s) : 3.0e38f;
+            float gate_d = 3.0e38f;
             double mprod = 1.0; int esum = 0;
             #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -489,9 +492,8 @@ k_analyse (const AnalyseParams p)
                     const ME q = me_from (mg);
                     mprod *= q.m;                                                                // >= 2^-8: no renormalisation needed
                     esum += q.e;
-                    e_budget += (q.e < 0 ? -q.e : q.e) + 1;
                 }
-                fgap = min (fgap, ulp_gap ((float) mg, eps_f));
+                gate_d = fminf (gate_d, fabsf (fabsf (cr[j]) - gate_s));
                 const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
                 weighted += fc * mg;
                 maxre = fmaxf (maxre, fabsf (cr[j]));
@@ -504,7 +506,7 @@ k_analyse (const AnalyseParams p)
             const float wmax = warp_max_nonneg (maxre);
             const float wraw = warp_max_nonneg (rawmax);
             const float wps = warp_sumf (psum);
-            const float wmar = ulps_to_margin (warp_minu (fgap));
+            const float wmar = warp_min_nonneg (fminf (gate_d * gate_inv, 0.5f));
             // inclusive warp scan of the extended-range product, in bin order
             ME inc = lprod;
             #pragma unroll
@@ -549,6 +551,15 @@ k_analyse (const AnalyseParams p)
         const float centroid = (float) (weighted / mag_sum);                                      // :127
         const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
         const double inv_max_e = 1.0 / max_e;
+        // how far 8 gated bins can move the exponent of the running flatness product: every gated magnitude lies in
+        // (eps, maxmag], so its exponent is bounded by the larger of the two ends' (CTA-uniform, no per-bin bookkeeping)
+        int e_budget = 0;
+        if (maxmag > 0.0)
+        {
+            const int e_hi = ((__double2hiint (maxmag) >> 20) & 0x7ff) - 1022;
+            const int e_lo = eps > 0.0 ? ((__double2hiint (eps) >> 20) & 0x7ff) - 1022 : -310;   // squares of fp32 values are >= 2^-298
+            e_budget = 8 * (max (abs (e_hi), abs (e_lo)) + 2);
+        }
 
         // =========================== pass 2: spread, slope sums, energy variance, flatness range events ===
         // :177 meanE = (sum of mag / maxE) / M.  The reference's third pass (:182-190, deviations from meanE) runs inside
