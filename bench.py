@@ -11,6 +11,8 @@ A "step" analyses the next 10 s of every track: K1 k_analyse (framing, 3 FFTs, a
   value  device-resident throughput (inputs already in HBM), CUDA events on the launching stream, max over ranks
   e2e    the same metric through the C-ABI call with HOST buffers (fx_analyse_host: pinned host audio in, smoothed
          features back out, copies inside the timed region)
+  e2e_pcm16  the same step from 16-bit PCM host buffers (fx_analyse_host_pcm, SURVEY.md 8f3 file ingest): the samples
+         cross the link at file width and are converted on the GPU (exactly, as JUCE's readers convert them)
   roofline      the binding roofline per BASELINE.json north_star: algorithmic FLOPs/frame (SURVEY.md 8d:
                 10 N log2 N + 48 N) x frames / live-measured k_analyse time vs an FP32 FMA microbenchmark on this GPU
   roofline_hbm  algorithmic bytes/frame (4 H + 40) x frames / the same time vs MEASURED_PEAKS.json hbm_gbs
@@ -188,6 +190,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pcm", action="store_true", help="skip the 16-bit PCM end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -276,6 +279,7 @@ def main():
 
     # ---- end to end through the C-ABI with host buffers ------------------------------------------------------
     e2e = None
+    e2e_pcm = None
     if not args.no_e2e:
         h_audio = torch.empty((T, S), dtype=torch.float32, pin_memory=True)
         h_audio.copy_(audio)
@@ -294,7 +298,32 @@ def main():
         e2e = {"value": frames_per_step * world * args.e2e_steps / float(t_e.item()), "unit": UNIT,
                "h2d_bytes_per_step": T * S * 4 * world, "d2h_bytes_per_step": T * F * 12 * 4 * world,
                "steps": args.e2e_steps, "api": "fx_analyse_host (pinned host audio in, smoothed features out)"}
-        del h_audio, h_smooth
+        e2e["h2d_gbs"] = e2e["h2d_bytes_per_step"] / world * args.e2e_steps / float(t_e.item()) / 1e9
+        e2e["note"] = ("fp32 host samples as the reference's audio callback delivers them (AudioDataCollector.h:36): "
+                       "bounded by the host->device link at 4 bytes/sample once the kernel outruns it")
+        del h_audio
+        # the same step from 16-bit PCM host buffers (file ingest, fx_analyse_host_pcm): half the bytes over the link;
+        # the device-resident workload is quantised to 16 bits on the host first, outside the timed region
+        if not args.no_pcm:
+            h_pcm = torch.empty((T, S), dtype=torch.int16, pin_memory=True)
+            h_pcm.copy_((audio.clamp(-1.0, 32767.0 / 32768.0) * 32768.0).round().to(torch.int16))
+            torch.cuda.synchronize(dev)
+            eng.analyse_host_pcm_ptr(h_pcm.data_ptr(), "s16le", 1, 0, S * 2, S, None, h_smooth.data_ptr(), None)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                eng.analyse_host_pcm_ptr(h_pcm.data_ptr(), "s16le", 1, 0, S * 2, S, None, h_smooth.data_ptr(), None)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            t_p = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+            e2e_pcm = {"value": frames_per_step * world * args.e2e_steps / float(t_p.item()), "unit": UNIT,
+                       "h2d_bytes_per_step": T * S * 2 * world, "d2h_bytes_per_step": T * F * 12 * 4 * world,
+                       "steps": args.e2e_steps, "h2d_gbs": T * S * 2 * args.e2e_steps / float(t_p.item()) / 1e9,
+                       "api": "fx_analyse_host_pcm (pinned host 16-bit PCM in, k_pcm_decode on the GPU, smoothed features out)"}
+            del h_pcm
+        del h_smooth
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------------
     cpu = None
@@ -316,7 +345,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, world),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "e2e_pcm16": e2e_pcm, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "k_analyse<16>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": traffic,
                          "peak_source": "FMA microbenchmark on this GPU (fx_measure_fp32_peak), measured",

@@ -73,7 +73,10 @@ struct fx_engine
     // host API pipeline
     float* d_audio_slot[3] = { nullptr, nullptr, nullptr };
     long   audio_slot_floats = 0;
-    cudaStream_t pipe_stream[3] = { nullptr, nullptr, nullptr };
+    unsigned char* d_pcm_slot[3] = { nullptr, nullptr, nullptr };     // file ingest: raw PCM rows of one track group
+    long   pcm_slot_bytes = 0;
+    cudaStream_t pipe_stream[3] = { nullptr, nullptr, nullptr };      // upload, analysis, download
+    cudaEvent_t  ev_ready[3] = { nullptr, nullptr, nullptr }, ev_free[3] = { nullptr, nullptr, nullptr };
 
     // streaming
     float* h_ring = nullptr;            // pinned [T][ring_len]
@@ -227,7 +230,18 @@ int choose_chunks (const fx_engine* e, long n_tracks, long frames)
     long c = (target + n_tracks - 1) / n_tracks;
     const long max_c = (frames + 7) / 8;
     if (c > max_c) c = max_c;
-    return (int) (c < 1 ? 1 : c);
+    if (c < 1) c = 1;
+    // among the next few chunk counts take the one whose last wave of CTAs is fullest (all CTAs carry equal work, so an
+    // almost empty last wave costs a whole chunk's time)
+    const long slots = (long) e->sm_count * e->ctas_per_sm;
+    long best_c = c; double best_fill = 0.0;
+    for (long k = c; k <= c + 4 && k <= max_c; ++k)
+    {
+        const long ctas = n_tracks * k, waves = (ctas + slots - 1) / slots;
+        const double fill = (double) ctas / (double) (waves * slots);
+        if (fill > best_fill + 1e-9) { best_fill = fill; best_c = k; }
+    }
+    return (int) best_c;
 }
 
 // K1 -> K2 -> K3 for tracks [t0, t0 + nt) on `s`.  Output pointers are already offset to track t0's rows.
@@ -303,7 +317,9 @@ void free_engine (fx_engine* e)
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
     cudaFree (e->d_raw); cudaFree (e->d_smooth); cudaFree (e->d_diag); cudaFree (e->d_latest); cudaFree (e->d_rec);
     if (e->h_latest) cudaFreeHost (e->h_latest);
+    for (int i = 0; i < 3; ++i) cudaFree (e->d_pcm_slot[i]);
     for (int i = 0; i < 3; ++i) { cudaFree (e->d_audio_slot[i]); if (e->pipe_stream[i]) cudaStreamDestroy (e->pipe_stream[i]); }
+    for (int i = 0; i < 3; ++i) { if (e->ev_ready[i]) cudaEventDestroy (e->ev_ready[i]); if (e->ev_free[i]) cudaEventDestroy (e->ev_free[i]); }
     if (e->h_ring) cudaFreeHost (e->h_ring);
     for (auto& g : e->groups) { cudaFree (g.d_stage); if (g.stream) cudaStreamDestroy (g.stream); }
     for (auto* v : { &e->prof_pending, &e->prof_free })
@@ -544,19 +560,29 @@ fx_status fx_analyse_device (fx_engine* e, const float* d_audio, long track_stri
     return FX_OK;
 }
 
-fx_status fx_analyse_host (fx_engine* e, const float* audio, long track_stride, long n_samples,
-                           float* raw, float* smooth, float* diag, long* n_frames)
+namespace {
+
+// Shared body of fx_analyse_host / fx_analyse_host_pcm.  format == 0: `src` is fp32, row stride in bytes = 4 * track_stride.
+fx_status analyse_host_impl (fx_engine* e, const unsigned char* src, long row_stride_bytes, int format, int n_channels, int channel,
+                             long n_samples, float* raw, float* smooth, float* diag, long* n_frames)
 {
-    if (! e || ! audio || n_samples < 0 || track_stride < n_samples) return FX_ERR_INVALID_ARG;
     FX_CUDA (e, cudaSetDevice (e->cfg.device));
     const long frames = n_samples / e->H;
     if (n_frames) *n_frames = frames;
     if (frames == 0) return FX_OK;
     const long T = e->cfg.n_tracks;
     const long used = frames * e->H;                                  // samples per track actually analysed
+    const long frame_bytes = format ? (long) n_channels * pcm_bytes_per_sample (format) : (long) sizeof (float);
+    const long row_bytes = used * frame_bytes;                        // source bytes per track that cross PCIe
 
-    // track groups sized so that a group's audio is ~64 MiB: big enough for PCIe efficiency, small enough to pipeline
-    long per = (64L << 20) / (used * (long) sizeof (float));
+    // Track groups: about thirty per call (the first group's upload and the last group's analysis are the only parts of
+    // the pipeline that do not overlap), but never below ~64 MiB of fp32 audio -- small groups would have to cut every
+    // track into short chunks to fill the GPU, and each chunk start refills a whole window
+    long want_groups = 32;
+    if (const char* env = getenv ("FXB200_PIPE_GROUPS")) { const long v = atol (env); if (v > 0) want_groups = v; }
+    long per = (T + want_groups - 1) / want_groups;
+    const long per_min = (64L << 20) / (used * (long) sizeof (float));
+    if (per < per_min) per = per_min;
     if (per < 1) per = 1;
     if (per > T) per = T;
     const long n_groups = (T + per - 1) / per;
@@ -568,6 +594,16 @@ fx_status fx_analyse_host (fx_engine* e, const float* audio, long track_stride, 
         e->audio_slot_floats = 0;
         for (int i = 0; i < 3; ++i) FX_CUDA (e, cudaMalloc (&e->d_audio_slot[i], (size_t) slot_floats * sizeof (float)));
         e->audio_slot_floats = slot_floats;
+    }
+    // PCM rows keep a 16-byte aligned pitch on the device so that the vector decode path applies whenever the format allows
+    const long pcm_pitch = (row_bytes + 15) & ~15L;
+    if (format && per * pcm_pitch > e->pcm_slot_bytes)
+    {
+        FX_CUDA (e, cudaDeviceSynchronize());
+        for (int i = 0; i < 3; ++i) { cudaFree (e->d_pcm_slot[i]); e->d_pcm_slot[i] = nullptr; }
+        e->pcm_slot_bytes = 0;
+        for (int i = 0; i < 3; ++i) FX_CUDA (e, cudaMalloc (&e->d_pcm_slot[i], (size_t) (per * pcm_pitch)));
+        e->pcm_slot_bytes = per * pcm_pitch;
     }
     for (int i = 0; i < 3; ++i)
         if (! e->pipe_stream[i]) FX_CUDA (e, cudaStreamCreateWithFlags (&e->pipe_stream[i], cudaStreamNonBlocking));
@@ -583,29 +619,119 @@ fx_status fx_analyse_host (fx_engine* e, const float* audio, long track_stride, 
     st = ensure_chunks (e, T * n_chunks);
     if (st != FX_OK) return st;
 
+    // Three streams, three slots: uploads, kernels and result downloads each run in group order on their own stream and
+    // meet through events, so that group g + 1's upload overlaps group g's analysis and the analysis kernels run back to
+    // back.  (Launching each group on its own stream lets the hardware interleave the CTAs of three analysis kernels: all
+    // three then finish together, their slots free together, and every third upload is exposed.)
+    cudaStream_t s_up = e->pipe_stream[0], s_run = e->pipe_stream[1], s_down = e->pipe_stream[2];
+    for (int i = 0; i < 3; ++i)
+    {
+        if (! e->ev_ready[i]) FX_CUDA (e, cudaEventCreateWithFlags (&e->ev_ready[i], cudaEventDisableTiming));
+        if (! e->ev_free[i])  FX_CUDA (e, cudaEventCreateWithFlags (&e->ev_free[i], cudaEventDisableTiming));
+    }
+    // FXB200_PIPE_TRACE=1: per-group device timeline of the pipeline on stderr (diagnostics)
+    const bool trace = getenv ("FXB200_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&] (cudaStream_t st_) { if (trace) { cudaEvent_t ev; cudaEventCreate (&ev); cudaEventRecord (ev, st_); tev.push_back (ev); } };
     for (long g = 0; g < n_groups; ++g)
     {
         const int slot = (int) (g % 3);
-        cudaStream_t s = e->pipe_stream[slot];
         const long t0 = g * per, nt = (t0 + per <= T) ? per : T - t0;
-        // stream order on `s` guarantees the slot's previous occupant (group g - 3) has been consumed
-        FX_CUDA (e, cudaMemcpy2DAsync (e->d_audio_slot[slot], (size_t) used * sizeof (float),
-                                        audio + t0 * track_stride, (size_t) track_stride * sizeof (float),
-                                        (size_t) used * sizeof (float), (size_t) nt, cudaMemcpyHostToDevice, s));
+        // upload: the slot's previous occupant (group g - 3) must have been analysed
+        if (g >= 3) FX_CUDA (e, cudaStreamWaitEvent (s_up, e->ev_free[slot], 0));
+        mark (s_up);
+        if (format == 0)
+            FX_CUDA (e, cudaMemcpy2DAsync (e->d_audio_slot[slot], (size_t) row_bytes, src + t0 * row_stride_bytes, (size_t) row_stride_bytes,
+                                            (size_t) row_bytes, (size_t) nt, cudaMemcpyHostToDevice, s_up));
+        else
+            FX_CUDA (e, cudaMemcpy2DAsync (e->d_pcm_slot[slot], (size_t) pcm_pitch, src + t0 * row_stride_bytes, (size_t) row_stride_bytes,
+                                            (size_t) row_bytes, (size_t) nt, cudaMemcpyHostToDevice, s_up));
+        mark (s_up);
+        FX_CUDA (e, cudaEventRecord (e->ev_ready[slot], s_up));
+        // analysis
+        FX_CUDA (e, cudaStreamWaitEvent (s_run, e->ev_ready[slot], 0));
+        if (format != 0)
+        {
+            PcmParams pp{};
+            pp.pcm = e->d_pcm_slot[slot]; pp.track_stride_bytes = pcm_pitch; pp.format = format; pp.n_channels = n_channels; pp.channel = channel;
+            pp.n_samples = used; pp.n_tracks = nt; pp.audio = e->d_audio_slot[slot]; pp.audio_stride = used;
+            FX_CUDA (e, launch_pcm_decode (pp, s_run));
+            e->launches += (uint64_t) pcm_launch_count (pp);
+        }
         const size_t roff = (size_t) t0 * (size_t) frames;
         float* dr = e->d_raw + roff * FX_NUM_FEATURES;
         float* ds = e->d_smooth + roff * FX_NUM_FEATURES;
         float* dd = e->d_diag + roff * FX_NUM_DIAG;
         st = run_range (e, (int) t0, (int) nt, n_chunks, e->d_audio_slot[slot], used, frames, dr, smooth ? ds : nullptr, diag ? dd : nullptr,
-                        e->d_latest + (size_t) t0 * (FX_NUM_FEATURES + 2), s);
+                        e->d_latest + (size_t) t0 * (FX_NUM_FEATURES + 2), s_run);
         if (st != FX_OK) return st;
-        if (raw)    FX_CUDA (e, cudaMemcpyAsync (raw + roff * FX_NUM_FEATURES, dr, (size_t) nt * frames * FX_NUM_FEATURES * sizeof (float), cudaMemcpyDeviceToHost, s));
-        if (smooth) FX_CUDA (e, cudaMemcpyAsync (smooth + roff * FX_NUM_FEATURES, ds, (size_t) nt * frames * FX_NUM_FEATURES * sizeof (float), cudaMemcpyDeviceToHost, s));
-        if (diag)   FX_CUDA (e, cudaMemcpyAsync (diag + roff * FX_NUM_DIAG, dd, (size_t) nt * frames * FX_NUM_DIAG * sizeof (float), cudaMemcpyDeviceToHost, s));
+        mark (s_run);
+        FX_CUDA (e, cudaEventRecord (e->ev_free[slot], s_run));
+        // results (engine-owned result buffers are indexed by track: no reuse inside a call)
+        FX_CUDA (e, cudaStreamWaitEvent (s_down, e->ev_free[slot], 0));
+        if (raw)    FX_CUDA (e, cudaMemcpyAsync (raw + roff * FX_NUM_FEATURES, dr, (size_t) nt * frames * FX_NUM_FEATURES * sizeof (float), cudaMemcpyDeviceToHost, s_down));
+        if (smooth) FX_CUDA (e, cudaMemcpyAsync (smooth + roff * FX_NUM_FEATURES, ds, (size_t) nt * frames * FX_NUM_FEATURES * sizeof (float), cudaMemcpyDeviceToHost, s_down));
+        if (diag)   FX_CUDA (e, cudaMemcpyAsync (diag + roff * FX_NUM_DIAG, dd, (size_t) nt * frames * FX_NUM_DIAG * sizeof (float), cudaMemcpyDeviceToHost, s_down));
+        mark (s_down);
     }
     for (int i = 0; i < 3; ++i) FX_CUDA (e, cudaStreamSynchronize (e->pipe_stream[i]));
+    if (trace)
+    {
+        for (size_t i = 0; i + 3 < tev.size(); i += 4)
+        {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime (&a, tev[0], tev[i]); cudaEventElapsedTime (&b, tev[0], tev[i + 1]);
+            cudaEventElapsedTime (&c, tev[0], tev[i + 2]); cudaEventElapsedTime (&d, tev[0], tev[i + 3]);
+            fprintf (stderr, "pipe group %3zu: upload %8.3f .. %8.3f  analysed %8.3f  results out %8.3f ms\n", i / 4, a, b, c, d);
+        }
+        for (auto ev : tev) cudaEventDestroy (ev);
+    }
     e->flip ^= 1;
     e->frames_done += frames;
+    return FX_OK;
+}
+
+} // namespace
+
+fx_status fx_analyse_host (fx_engine* e, const float* audio, long track_stride, long n_samples,
+                           float* raw, float* smooth, float* diag, long* n_frames)
+{
+    if (! e || ! audio || n_samples < 0 || track_stride < n_samples) return FX_ERR_INVALID_ARG;
+    return analyse_host_impl (e, reinterpret_cast<const unsigned char*> (audio), track_stride * (long) sizeof (float), 0, 1, 0,
+                              n_samples, raw, smooth, diag, n_frames);
+}
+
+// ---- file ingest ----------------------------------------------------------------------------------------
+int fx_pcm_bytes_per_sample (int format) { return fx::pcm_bytes_per_sample (format); }
+
+fx_status fx_analyse_host_pcm (fx_engine* e, const void* pcm, int format, int n_channels, int channel,
+                               long track_stride_bytes, long n_samples,
+                               float* raw, float* smooth, float* diag, long* n_frames)
+{
+    const int bps = fx::pcm_bytes_per_sample (format);
+    if (! e || ! pcm || n_samples < 0 || n_channels < 1 || channel < 0 || channel >= n_channels) return FX_ERR_INVALID_ARG;
+    if (bps == 0) return FX_ERR_UNSUPPORTED;
+    if (track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
+    return analyse_host_impl (e, static_cast<const unsigned char*> (pcm), track_stride_bytes, format, n_channels, channel,
+                              n_samples, raw, smooth, diag, n_frames);
+}
+
+fx_status fx_decode_pcm_device (fx_engine* e, const void* d_pcm, int format, int n_channels, int channel,
+                                long track_stride_bytes, long n_samples, long n_tracks,
+                                float* d_audio, long audio_stride, void* stream)
+{
+    const int bps = fx::pcm_bytes_per_sample (format);
+    if (! e || ! d_pcm || ! d_audio || n_samples < 0 || n_tracks < 0 || n_channels < 1 || channel < 0 || channel >= n_channels
+        || audio_stride < n_samples) return FX_ERR_INVALID_ARG;
+    if (bps == 0) return FX_ERR_UNSUPPORTED;
+    if (n_tracks > 1 && track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
+    FX_CUDA (e, cudaSetDevice (e->cfg.device));
+    PcmParams pp{};
+    pp.pcm = static_cast<const unsigned char*> (d_pcm); pp.track_stride_bytes = track_stride_bytes; pp.format = format;
+    pp.n_channels = n_channels; pp.channel = channel; pp.n_samples = n_samples; pp.n_tracks = n_tracks;
+    pp.audio = d_audio; pp.audio_stride = audio_stride;
+    FX_CUDA (e, launch_pcm_decode (pp, stream ? static_cast<cudaStream_t> (stream) : e->stream));
+    e->launches += (uint64_t) pcm_launch_count (pp);
     return FX_OK;
 }
 

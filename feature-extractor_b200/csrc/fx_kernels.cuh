@@ -103,6 +103,33 @@ struct SmoothParams
 };
 cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t stream);
 
+// ---- K0: file ingest, interleaved PCM -> track-major fp32 (fx_pcm.cu) ----------------------------------
+struct PcmParams
+{
+    const unsigned char* pcm;      // [n_tracks] rows of interleaved sample frames, track_stride_bytes apart
+    long         track_stride_bytes;
+    int          format;           // FX_PCM_*
+    int          n_channels;       // samples per frame in the source
+    int          channel;          // the one channel each track analyses (AudioDataCollector.h:42-43)
+    long         n_samples;        // frames to decode per track
+    long         n_tracks;
+    float*       audio;            // [n_tracks][audio_stride]
+    long         audio_stride;
+};
+cudaError_t launch_pcm_decode (const PcmParams& p, cudaStream_t stream);
+int         pcm_launch_count (const PcmParams& p);
+__host__ __device__ inline int pcm_bytes_per_sample (int format)
+{
+    switch (format)
+    {
+        case FX_PCM_U8: case FX_PCM_S8:                                               return 1;
+        case FX_PCM_S16LE: case FX_PCM_S16BE:                                         return 2;
+        case FX_PCM_S24LE: case FX_PCM_S24BE:                                         return 3;
+        case FX_PCM_S32LE: case FX_PCM_S32BE: case FX_PCM_F32LE: case FX_PCM_F32BE:   return 4;
+        default:                                                                      return 0;
+    }
+}
+
 // ---- synthetic workload ------------------------------------------------------------------------------
 cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
                           double sample_rate, uint64_t seed, cudaStream_t stream);

@@ -31,7 +31,11 @@ EXPORTS = (
     "fx_set_onset", "fx_reset", "fx_analyse_host", "fx_analyse_device", "fx_push_block", "fx_process",
     "fx_poll_features", "fx_flush", "fx_osc_order", "fx_synth_device", "fx_kernel_launches",
     "fx_profile_enable", "fx_profile_read", "fx_measure_fp32_peak",
+    "fx_pcm_bytes_per_sample", "fx_analyse_host_pcm", "fx_decode_pcm_device",
 )
+
+# fx_engine.h FX_PCM_*: sample encodings of WAV (little endian) and AIFF (big endian) data chunks
+PCM_FORMATS = {"u8": 1, "s8": 2, "s16le": 3, "s16be": 4, "s24le": 5, "s24be": 6, "s32le": 7, "s32be": 8, "f32le": 9, "f32be": 10}
 
 
 class Config(ctypes.Structure):
@@ -99,6 +103,12 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.fx_profile_read.restype = c_int
     lib.fx_measure_fp32_peak.argtypes = [c_int, POINTER(c_double)]
     lib.fx_measure_fp32_peak.restype = c_int
+    lib.fx_pcm_bytes_per_sample.argtypes = [c_int]
+    lib.fx_pcm_bytes_per_sample.restype = c_int
+    lib.fx_analyse_host_pcm.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_void_p, c_void_p, c_void_p, POINTER(c_long)]
+    lib.fx_analyse_host_pcm.restype = c_int
+    lib.fx_decode_pcm_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_void_p, c_long, c_void_p]
+    lib.fx_decode_pcm_device.restype = c_int
     if path is None:
         _lib = lib
     return lib
@@ -183,6 +193,43 @@ class Engine:
         st = self.lib.fx_analyse_host(self._h, audio_ptr, track_stride, n_samples, raw_ptr, smooth_ptr, diag_ptr, ctypes.byref(nf))
         self._check(st, "fx_analyse_host")
         return nf.value
+
+    # -- file ingest: interleaved PCM rows (bytes as they lie in a WAV / AIFF data chunk) ------------------------
+    def analyse_host_pcm(self, pcm: np.ndarray, fmt: str, n_channels: int = 1, channel: int = 0,
+                         want_raw=True, want_smooth=True, want_diag=True):
+        """pcm: uint8 [n_tracks, row_bytes]; each row holds sample frames of n_channels interleaved samples."""
+        b = np.ascontiguousarray(pcm).view(np.uint8)
+        if b.ndim != 2 or b.shape[0] != self.cfg.n_tracks:
+            raise ValueError("pcm must be [n_tracks, row_bytes]")
+        code = PCM_FORMATS[fmt]
+        bps = self.lib.fx_pcm_bytes_per_sample(code)
+        T, row = b.shape
+        S = row // (bps * n_channels)
+        F = S // self.cfg.hop
+        raw = np.empty((T, F, NUM_FEATURES), np.float32) if want_raw else None
+        smooth = np.empty((T, F, NUM_FEATURES), np.float32) if want_smooth else None
+        diag = np.empty((T, F, NUM_DIAG), np.float32) if want_diag else None
+        nf = c_long(0)
+        st = self.lib.fx_analyse_host_pcm(self._h, b.ctypes.data, code, n_channels, channel, row, S,
+                                          raw.ctypes.data if want_raw else None,
+                                          smooth.ctypes.data if want_smooth else None,
+                                          diag.ctypes.data if want_diag else None, ctypes.byref(nf))
+        self._check(st, "fx_analyse_host_pcm")
+        assert nf.value == F
+        return {"raw": raw, "smooth": smooth, "diag": diag, "frames": F}
+
+    def analyse_host_pcm_ptr(self, pcm_ptr: int, fmt: str, n_channels: int, channel: int, track_stride_bytes: int, n_samples: int,
+                             raw_ptr=None, smooth_ptr=None, diag_ptr=None) -> int:
+        nf = c_long(0)
+        st = self.lib.fx_analyse_host_pcm(self._h, pcm_ptr, PCM_FORMATS[fmt], n_channels, channel, track_stride_bytes, n_samples,
+                                          raw_ptr, smooth_ptr, diag_ptr, ctypes.byref(nf))
+        self._check(st, "fx_analyse_host_pcm")
+        return nf.value
+
+    def decode_pcm_device(self, d_pcm_ptr: int, fmt: str, n_channels: int, channel: int, track_stride_bytes: int, n_samples: int,
+                          n_tracks: int, d_audio_ptr: int, audio_stride: int, stream: int | None = None):
+        self._check(self.lib.fx_decode_pcm_device(self._h, d_pcm_ptr, PCM_FORMATS[fmt], n_channels, channel, track_stride_bytes,
+                                                  n_samples, n_tracks, d_audio_ptr, audio_stride, stream), "fx_decode_pcm_device")
 
     # -- batch analysis, device buffers (raw pointers; torch is only used by callers for allocation) ----------
     def analyse_device(self, d_audio_ptr: int, track_stride: int, n_samples: int, d_raw_ptr=None, d_smooth_ptr=None,

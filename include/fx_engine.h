@@ -115,6 +115,30 @@ fx_status   fx_analyse_host   (fx_engine* e, const float* audio, long track_stri
 fx_status   fx_analyse_device (fx_engine* e, const float* d_audio, long track_stride, long n_samples,
                                float* d_raw, float* d_smooth, float* d_diag, void* stream, long* n_frames);
 
+/* ---- file ingest: PCM in, features out ---------------------------------------------------------------
+ * Replaces the file route of the reference: AudioFilePlayer::loadFileIntoTransport (AudioFilePlayer.h:41-60) hands the
+ * file to JUCE's format readers, the transport plays it through the device output and AudioDataCollector re-captures one
+ * output channel (AudioDataCollector.h:42-43).  Here the bytes of the file's data chunk go to the GPU as they are
+ * (interleaved sample frames, WAV little endian / AIFF big endian), kernel k_pcm_decode converts the one channel each
+ * track analyses to fp32 exactly as JUCE's readers do ((float) left-justified int32 * (1.0f / 0x7fffffff); 8-bit WAV is
+ * offset binary; float data passes through), and the analysis runs on the result.  Integer samples of <= 24 bits
+ * convert exactly, so a 16-bit file crosses PCIe at 2 bytes per sample and still yields the fp32 input the
+ * float API would have been given. */
+enum {
+    FX_PCM_U8 = 1, FX_PCM_S8, FX_PCM_S16LE, FX_PCM_S16BE, FX_PCM_S24LE, FX_PCM_S24BE,
+    FX_PCM_S32LE, FX_PCM_S32BE, FX_PCM_F32LE, FX_PCM_F32BE
+};
+int         fx_pcm_bytes_per_sample (int format);        /* 0 for an unknown format */
+/* pcm holds n_tracks rows, track_stride_bytes apart; each row is n_samples sample frames of n_channels interleaved
+ * samples, of which `channel` is analysed.  Otherwise as fx_analyse_host (HOST pointers, pipelined copies, state carries
+ * over).  fx_decode_pcm_device is the conversion alone on DEVICE pointers, asynchronous on `stream`. */
+fx_status   fx_analyse_host_pcm  (fx_engine* e, const void* pcm, int format, int n_channels, int channel,
+                                  long track_stride_bytes, long n_samples,
+                                  float* raw, float* smooth, float* diag, long* n_frames);
+fx_status   fx_decode_pcm_device (fx_engine* e, const void* d_pcm, int format, int n_channels, int channel,
+                                  long track_stride_bytes, long n_samples, long n_tracks,
+                                  float* d_audio, long audio_stride, void* stream);
+
 /* ---- real-time path --------------------------------------------------------------------------------
  * fx_push_block replaces AudioDataCollector::audioDeviceIOCallback (AudioDataCollector.h:36-70) for a
  * range of tracks: copies n_samples of each channel into the pinned host ring (wait-free: memcpy + index

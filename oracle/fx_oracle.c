@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <stdint.h>
 #include "fx_oracle_api.h"
 
 #define FX_PI_D 3.1415926535897932384626433832795
@@ -753,4 +754,37 @@ void fxo_fft_inverse (float* inout_2n, int n)
     fft_plan_init (&p, n, 1);
     fft_real_inverse (&p, inout_2n, scratch);
     fft_plan_free (&p); free (scratch);
+}
+
+/* ---- file ingest: PCM decode ------------------------------------------------------------------------------
+ * juce::AudioFormatReader::read [JUCE-recall, juce_audio_formats 4.2.3; not vendored under /root/reference]: the WAV /
+ * AIFF readers left-justify integer samples into int32 (8-bit WAV is unsigned with a 128 offset) and the float conversion
+ * multiplies (float) int32 by 1.0f / 0x7fffffff, which is exactly 2^-31 in fp32.  Parity unpinned: the reference holds
+ * no test or fixture for this conversion; AudioFilePlayer (AudioFilePlayer.h:41-60) only hands the file to JUCE. */
+long fxo_pcm_decode (const void* pcm, int format, int n_channels, int channel, long n_samples, float* out)
+{
+    static const int bytes[11] = { 0, 1, 1, 2, 2, 3, 3, 4, 4, 4, 4 };
+    if (! pcm || ! out || format < 1 || format > 10 || n_channels < 1 || channel < 0 || channel >= n_channels || n_samples < 0) return -1;
+    const int bps = bytes[format];
+    const unsigned char* b = (const unsigned char*) pcm;
+    const float scale = 1.0f / 0x7fffffff;
+    for (long i = 0; i < n_samples; ++i)
+    {
+        const unsigned char* q = b + ((size_t) i * (size_t) n_channels + (size_t) channel) * (size_t) bps;
+        uint32_t u = 0;
+        switch (format)
+        {
+            case 1:  u = (uint32_t) (q[0] ^ 0x80u) << 24; break;                                        /* offset binary */
+            case 2:  u = (uint32_t) q[0] << 24; break;
+            case 3:  u = ((uint32_t) q[0] << 16) | ((uint32_t) q[1] << 24); break;
+            case 4:  u = ((uint32_t) q[1] << 16) | ((uint32_t) q[0] << 24); break;
+            case 5:  u = ((uint32_t) q[0] << 8) | ((uint32_t) q[1] << 16) | ((uint32_t) q[2] << 24); break;
+            case 6:  u = ((uint32_t) q[2] << 8) | ((uint32_t) q[1] << 16) | ((uint32_t) q[0] << 24); break;
+            case 7:  case 9:  u = (uint32_t) q[0] | ((uint32_t) q[1] << 8) | ((uint32_t) q[2] << 16) | ((uint32_t) q[3] << 24); break;
+            default: u = (uint32_t) q[3] | ((uint32_t) q[2] << 8) | ((uint32_t) q[1] << 16) | ((uint32_t) q[0] << 24); break;
+        }
+        if (format >= 9) { float f; memcpy (&f, &u, 4); out[i] = f; }
+        else             out[i] = (float) (int32_t) u * scale;
+    }
+    return n_samples;
 }

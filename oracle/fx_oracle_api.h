@@ -68,6 +68,13 @@ long fxo_analyse_tracks (const fxo_config* cfg, const float* audio, long n_track
 void fxo_fft_forward (const float* frame, int n, float* out_2n);
 void fxo_fft_inverse (float* inout_2n, int n);
 
+/* File ingest (port only): decode n_samples frames of interleaved PCM, taking one channel, to the fp32 samples the
+ * analysis consumes.  Restates what juce::AudioFormatReader::read does for the formats registerBasicFormats() offers to
+ * AudioFilePlayer (AudioFilePlayer.h:17,47) [JUCE-recall; JUCE is not under /root/reference]: integer samples are
+ * left-justified into int32 and scaled by 1.0f / 0x7fffffff (= 2^-31 in fp32); 8-bit WAV is offset binary; floats pass through.
+ * Formats: 1 U8, 2 S8, 3 S16LE, 4 S16BE, 5 S24LE, 6 S24BE, 7 S32LE, 8 S32BE, 9 F32LE, 10 F32BE.  Returns n_samples or -1. */
+long fxo_pcm_decode (const void* pcm, int format, int n_channels, int channel, long n_samples, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,45 @@ def port() -> Oracle:
     return Oracle(PORT_SO)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# file ingest (port only: the conversion lives in JUCE, not under /root/reference)
+PCM_FORMATS = {"u8": 1, "s8": 2, "s16le": 3, "s16be": 4, "s24le": 5, "s24be": 6, "s32le": 7, "s32be": 8, "f32le": 9, "f32be": 10}
+PCM_BYTES = {"u8": 1, "s8": 1, "s16le": 2, "s16be": 2, "s24le": 3, "s24be": 3, "s32le": 4, "s32be": 4, "f32le": 4, "f32be": 4}
+
+
+def pcm_decode(pcm_row: np.ndarray, fmt: str, n_channels: int = 1, channel: int = 0) -> np.ndarray:
+    """Decode one row of interleaved PCM bytes with the C port (oracle/fx_oracle.c: fxo_pcm_decode)."""
+    lib = port().lib
+    lib.fxo_pcm_decode.restype = ctypes.c_long
+    lib.fxo_pcm_decode.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_void_p]
+    b = np.ascontiguousarray(pcm_row).view(np.uint8).ravel()
+    n = len(b) // (PCM_BYTES[fmt] * n_channels)
+    out = np.empty(n, np.float32)
+    r = lib.fxo_pcm_decode(b.ctypes.data, PCM_FORMATS[fmt], n_channels, channel, n, out.ctypes.data)
+    assert r == n
+    return out
+
+
+def pcm_encode(x: np.ndarray, fmt: str, seed: int = 0) -> np.ndarray:
+    """Quantise float samples in [-1, 1) to `fmt` (test-vector generator, numpy only): returns uint8 bytes, sample-major."""
+    x = np.asarray(x, np.float64)
+    if fmt.startswith("f32"):
+        v = x.astype("<f4" if fmt.endswith("le") else ">f4")
+        return v.view(np.uint8).reshape(*x.shape[:-1], -1) if x.ndim > 1 else v.view(np.uint8)
+    bits = {"u8": 8, "s8": 8}.get(fmt) or int(fmt[1:3])
+    q = np.clip(np.round(x * (1 << (bits - 1))), -(1 << (bits - 1)), (1 << (bits - 1)) - 1).astype(np.int64)
+    if fmt == "u8":
+        return (q + 128).astype(np.uint8)
+    if fmt == "s8":
+        return q.astype(np.int8).view(np.uint8)
+    nb = bits // 8
+    u = (q & ((1 << bits) - 1)).astype(np.uint64)
+    by = np.stack([((u >> (8 * i)) & 0xFF).astype(np.uint8) for i in range(nb)], axis=-1)      # little endian
+    if fmt.endswith("be"):
+        by = by[..., ::-1]
+    return np.ascontiguousarray(by).reshape(*x.shape[:-1], -1)
+
+
 def reference() -> Oracle | None:
     """The reference's own headers compiled headless (prebuilt in this container; travels to the GPU box)."""
     return Oracle(REF_SO) if os.path.exists(REF_SO) else None
