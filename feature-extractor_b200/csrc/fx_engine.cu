@@ -574,6 +574,7 @@ fx_status analyse_host_impl (fx_engine* e, const unsigned char* src, long row_st
     const long used = frames * e->H;                                  // samples per track actually analysed
     const long frame_bytes = format ? (long) n_channels * pcm_bytes_per_sample (format) : (long) sizeof (float);
     const long row_bytes = used * frame_bytes;                        // source bytes per track that cross PCIe
+    const bool shared_row = format != 0 && row_stride_bytes == 0;     // every track reads the same interleaved stream
 
     // Track groups: about thirty per call (the first group's upload and the last group's analysis are the only parts of
     // the pipeline that do not overlap), but never below ~64 MiB of fp32 audio -- small groups would have to cut every
@@ -643,6 +644,8 @@ fx_status analyse_host_impl (fx_engine* e, const unsigned char* src, long row_st
         if (format == 0)
             FX_CUDA (e, cudaMemcpy2DAsync (e->d_audio_slot[slot], (size_t) row_bytes, src + t0 * row_stride_bytes, (size_t) row_stride_bytes,
                                             (size_t) row_bytes, (size_t) nt, cudaMemcpyHostToDevice, s_up));
+        else if (shared_row)       // one interleaved stream feeds every track (track t <- channel t % n_channels): upload it once per group
+            FX_CUDA (e, cudaMemcpyAsync (e->d_pcm_slot[slot], src, (size_t) row_bytes, cudaMemcpyHostToDevice, s_up));
         else
             FX_CUDA (e, cudaMemcpy2DAsync (e->d_pcm_slot[slot], (size_t) pcm_pitch, src + t0 * row_stride_bytes, (size_t) row_stride_bytes,
                                             (size_t) row_bytes, (size_t) nt, cudaMemcpyHostToDevice, s_up));
@@ -653,7 +656,8 @@ fx_status analyse_host_impl (fx_engine* e, const unsigned char* src, long row_st
         if (format != 0)
         {
             PcmParams pp{};
-            pp.pcm = e->d_pcm_slot[slot]; pp.track_stride_bytes = pcm_pitch; pp.format = format; pp.n_channels = n_channels; pp.channel = channel;
+            pp.pcm = e->d_pcm_slot[slot]; pp.track_stride_bytes = shared_row ? 0 : pcm_pitch; pp.format = format; pp.n_channels = n_channels;
+            pp.channel = channel; pp.first_track = t0;
             pp.n_samples = used; pp.n_tracks = nt; pp.audio = e->d_audio_slot[slot]; pp.audio_stride = used;
             FX_CUDA (e, launch_pcm_decode (pp, s_run));
             e->launches += (uint64_t) pcm_launch_count (pp);
@@ -709,9 +713,9 @@ fx_status fx_analyse_host_pcm (fx_engine* e, const void* pcm, int format, int n_
                                float* raw, float* smooth, float* diag, long* n_frames)
 {
     const int bps = fx::pcm_bytes_per_sample (format);
-    if (! e || ! pcm || n_samples < 0 || n_channels < 1 || channel < 0 || channel >= n_channels) return FX_ERR_INVALID_ARG;
+    if (! e || ! pcm || n_samples < 0 || n_channels < 1 || channel < -1 || channel >= n_channels) return FX_ERR_INVALID_ARG;
     if (bps == 0) return FX_ERR_UNSUPPORTED;
-    if (track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
+    if (track_stride_bytes != 0 && track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
     return analyse_host_impl (e, static_cast<const unsigned char*> (pcm), track_stride_bytes, format, n_channels, channel,
                               n_samples, raw, smooth, diag, n_frames);
 }
@@ -721,10 +725,10 @@ fx_status fx_decode_pcm_device (fx_engine* e, const void* d_pcm, int format, int
                                 float* d_audio, long audio_stride, void* stream)
 {
     const int bps = fx::pcm_bytes_per_sample (format);
-    if (! e || ! d_pcm || ! d_audio || n_samples < 0 || n_tracks < 0 || n_channels < 1 || channel < 0 || channel >= n_channels
+    if (! e || ! d_pcm || ! d_audio || n_samples < 0 || n_tracks < 0 || n_channels < 1 || channel < -1 || channel >= n_channels
         || audio_stride < n_samples) return FX_ERR_INVALID_ARG;
     if (bps == 0) return FX_ERR_UNSUPPORTED;
-    if (n_tracks > 1 && track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
+    if (n_tracks > 1 && track_stride_bytes != 0 && track_stride_bytes < n_samples * (long) n_channels * bps) return FX_ERR_INVALID_ARG;
     FX_CUDA (e, cudaSetDevice (e->cfg.device));
     PcmParams pp{};
     pp.pcm = static_cast<const unsigned char*> (d_pcm); pp.track_stride_bytes = track_stride_bytes; pp.format = format;

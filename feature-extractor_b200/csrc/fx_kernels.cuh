@@ -110,7 +110,8 @@ struct PcmParams
     long         track_stride_bytes;
     int          format;           // FX_PCM_*
     int          n_channels;       // samples per frame in the source
-    int          channel;          // the one channel each track analyses (AudioDataCollector.h:42-43)
+    int          channel;          // the one channel each track analyses (AudioDataCollector.h:42-43); -1: track t takes channel (first_track + t) % n_channels
+    long         first_track;      // engine index of row 0 (only used by channel == -1)
     long         n_samples;        // frames to decode per track
     long         n_tracks;
     float*       audio;            // [n_tracks][audio_stride]

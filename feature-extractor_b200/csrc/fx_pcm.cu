@@ -60,7 +60,8 @@ __global__ void __launch_bounds__ (256) k_pcm_decode (const PcmParams p, long fi
     const long track = idx / quads, i0 = first_sample + ((idx % quads) << 2);
     const int bps = pcm_bytes_per_sample (p.format);
     const long frame_bytes = (long) p.n_channels * bps;
-    const uint8_t* src = p.pcm + track * p.track_stride_bytes + (long) p.channel * bps;
+    const int ch = p.channel >= 0 ? p.channel : (int) ((p.first_track + track) % p.n_channels);
+    const uint8_t* src = p.pcm + track * p.track_stride_bytes + (long) ch * bps;
     float* dst = p.audio + track * p.audio_stride;
     #pragma unroll
     for (int u = 0; u < 4; ++u)

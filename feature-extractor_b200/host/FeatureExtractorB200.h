@@ -25,6 +25,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -91,6 +92,7 @@ public:
         setup.bufferSize = bufferSize;
         setup.sampleRate = sampleRate;
         numChannels = numInputChannels;
+        hopSize = cfg.hop;
         if (fx_engine_create (&cfg, &engine) != FX_OK)
             throw std::runtime_error (String ("fx_engine_create: ") + fx_last_error (nullptr));   // no CPU fallback
     }
@@ -139,6 +141,7 @@ public:
 
     fx_engine* getEngine() const noexcept { return engine; }
     int getNumInputChannels() const noexcept { return numChannels; }
+    long getHopSize() const noexcept { return hopSize; }
     void setAnalysing (bool on) noexcept { analysing = on; }
 
     // one collector per track feeds the ring; the reference's second collector per track carries the same samples
@@ -158,6 +161,7 @@ private:
     fx_engine* engine = nullptr;
     AudioDeviceSetup setup;
     int numChannels = 0;
+    long hopSize = 0;
     bool analysing = true;
     bool wakeRequested = false;
     std::vector<std::pair<const void*, std::function<void()>>> afterAnalysis;
@@ -457,6 +461,199 @@ public:
 
 private:
     int sock = -1;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// AudioFormatReader: what AudioFormatManager::createReaderFor (AudioFilePlayer.h:47, after registerBasicFormats :17) yields
+// for the two basic formats the reference can open -- WAV (RIFF/WAVE: PCM, IEEE float, WAVE_FORMAT_EXTENSIBLE) and AIFF /
+// AIFF-C ('NONE', 'sowt', 'fl32').  Only the container is parsed on the host; the sample data stays as it lies in the file
+// and is converted on the GPU (kernel k_pcm_decode behind fx_analyse_host_pcm).
+class AudioFormatReader
+{
+public:
+    double  sampleRate = 0.0;
+    int     numChannels = 0;
+    int     bitsPerSample = 0;
+    bool    usesFloatingPointData = false;
+    long    lengthInSamples = 0;                  // sample frames
+    int     pcmFormat = 0;                        // FX_PCM_*
+    String  formatName;                           // "WAV file" / "AIFF file" as JUCE names them
+
+    const uint8_t* data() const noexcept { return file.data() + dataOffset; }
+    size_t dataBytes() const noexcept { return (size_t) lengthInSamples * (size_t) numChannels * (size_t) fx_pcm_bytes_per_sample (pcmFormat); }
+
+    // nullptr when the file cannot be opened or is not a WAV / AIFF this reader understands (as createReaderFor does)
+    static std::unique_ptr<AudioFormatReader> createReaderFor (const String& path)
+    {
+        FILE* f = fopen (path.c_str(), "rb");
+        if (! f) return nullptr;
+        std::unique_ptr<AudioFormatReader> r (new AudioFormatReader);
+        fseek (f, 0, SEEK_END);
+        const long size = ftell (f);
+        fseek (f, 0, SEEK_SET);
+        if (size < 12) { fclose (f); return nullptr; }
+        r->file.resize ((size_t) size);
+        const bool ok = fread (r->file.data(), 1, (size_t) size, f) == (size_t) size;
+        fclose (f);
+        if (! ok) return nullptr;
+        return (r->parseWav() || r->parseAiff()) ? std::move (r) : nullptr;
+    }
+    static std::unique_ptr<AudioFormatReader> createReaderFor (std::vector<uint8_t> bytes)
+    {
+        std::unique_ptr<AudioFormatReader> r (new AudioFormatReader);
+        r->file = std::move (bytes);
+        return (r->file.size() >= 12 && (r->parseWav() || r->parseAiff())) ? std::move (r) : nullptr;
+    }
+
+private:
+    std::vector<uint8_t> file;
+    size_t dataOffset = 0;
+
+    bool tag (size_t at, const char* four) const { return at + 4 <= file.size() && memcmp (file.data() + at, four, 4) == 0; }
+    uint32_t le32 (size_t at) const { return (uint32_t) file[at] | ((uint32_t) file[at + 1] << 8) | ((uint32_t) file[at + 2] << 16) | ((uint32_t) file[at + 3] << 24); }
+    uint16_t le16 (size_t at) const { return (uint16_t) (file[at] | (file[at + 1] << 8)); }
+    uint32_t be32 (size_t at) const { return (uint32_t) file[at + 3] | ((uint32_t) file[at + 2] << 8) | ((uint32_t) file[at + 1] << 16) | ((uint32_t) file[at] << 24); }
+    uint16_t be16 (size_t at) const { return (uint16_t) (file[at + 1] | (file[at] << 8)); }
+
+    bool finish (size_t offset, size_t bytes, int bits, bool isFloat, bool bigEndian, bool eightBitSigned)
+    {
+        int fmt = 0;
+        if (isFloat)        fmt = bits == 32 ? (bigEndian ? FX_PCM_F32BE : FX_PCM_F32LE) : 0;
+        else if (bits == 8) fmt = eightBitSigned ? FX_PCM_S8 : FX_PCM_U8;
+        else if (bits == 16) fmt = bigEndian ? FX_PCM_S16BE : FX_PCM_S16LE;
+        else if (bits == 24) fmt = bigEndian ? FX_PCM_S24BE : FX_PCM_S24LE;
+        else if (bits == 32) fmt = bigEndian ? FX_PCM_S32BE : FX_PCM_S32LE;
+        if (fmt == 0 || numChannels < 1 || sampleRate <= 0.0 || offset > file.size()) return false;
+        if (bytes > file.size() - offset) bytes = file.size() - offset;           // truncated file: read what is there
+        pcmFormat = fmt; bitsPerSample = bits; usesFloatingPointData = isFloat; dataOffset = offset;
+        lengthInSamples = (long) (bytes / ((size_t) numChannels * (size_t) fx_pcm_bytes_per_sample (fmt)));
+        return true;
+    }
+
+    bool parseWav()
+    {
+        if (! (tag (0, "RIFF") && tag (8, "WAVE"))) return false;
+        size_t at = 12;
+        int formatTag = 0, bits = 0;
+        bool haveFmt = false;
+        while (at + 8 <= file.size())
+        {
+            const size_t len = le32 (at + 4), body = at + 8;
+            if (tag (at, "fmt ") && body + 16 <= file.size())
+            {
+                formatTag = le16 (body); numChannels = le16 (body + 2); sampleRate = (double) le32 (body + 4); bits = le16 (body + 14);
+                if (formatTag == 0xFFFE && len >= 40 && body + 26 <= file.size()) formatTag = le16 (body + 24);      // sub-format GUID, first two bytes
+                haveFmt = true;
+            }
+            else if (tag (at, "data") && haveFmt)
+            {
+                formatName = "WAV file";
+                return (formatTag == 1 || formatTag == 3) && finish (body, len, bits, formatTag == 3, false, false);
+            }
+            at = body + len + (len & 1u);                                         // chunks are word aligned
+        }
+        return false;
+    }
+
+    static double extended80 (const uint8_t* b)                                    // the AIFF sample rate
+    {
+        const int exponent = ((b[0] & 0x7f) << 8) | b[1];
+        uint64_t mant = 0;
+        for (int i = 0; i < 8; ++i) mant = (mant << 8) | b[2 + i];
+        if (exponent == 0 && mant == 0) return 0.0;
+        return std::ldexp ((double) mant, exponent - 16383 - 63) * ((b[0] & 0x80) ? -1.0 : 1.0);
+    }
+
+    bool parseAiff()
+    {
+        if (! (tag (0, "FORM") && (tag (8, "AIFF") || tag (8, "AIFC")))) return false;
+        const bool aifc = tag (8, "AIFC");
+        size_t at = 12;
+        int bits = 0; uint32_t frames = 0; bool haveComm = false, littleEndian = false, isFloat = false;
+        while (at + 8 <= file.size())
+        {
+            const size_t len = be32 (at + 4), body = at + 8;
+            if (tag (at, "COMM") && body + 18 <= file.size())
+            {
+                numChannels = be16 (body); frames = be32 (body + 2); bits = be16 (body + 6); sampleRate = extended80 (file.data() + body + 8);
+                if (aifc && len >= 22 && body + 22 <= file.size())
+                {
+                    if (tag (body + 18, "sowt")) littleEndian = true;
+                    else if (tag (body + 18, "fl32") || tag (body + 18, "FL32")) isFloat = true;
+                    else if (! tag (body + 18, "NONE")) return false;             // compressed AIFF-C
+                }
+                haveComm = true;
+            }
+            else if (tag (at, "SSND") && haveComm && body + 8 <= file.size())
+            {
+                const size_t offset = be32 (body);
+                formatName = "AIFF file";
+                const size_t bps = (size_t) ((bits + 7) / 8);
+                return finish (body + 8 + offset, (size_t) frames * (size_t) numChannels * bps, (int) bps * 8, isFloat, ! littleEndian, true);
+            }
+            at = body + len + (len & 1u);
+        }
+        return false;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// AudioFilePlayer (AudioFilePlayer.h:14-78).  The reference plays the file through the device output and the collectors
+// re-capture one output channel per track (AudioDataCollector.h:42-43); here the loaded file is analysed in one call:
+// track t of the engine takes channel t % numChannels of the file, the PCM goes to the GPU at its file width.
+// The transport surface (play / pause / stop / restart / hasFile) is kept; it selects what analyseLoadedFile() covers.
+class AudioFilePlayer
+{
+public:
+    AudioFilePlayer() = default;
+    AudioFilePlayer (const AudioFilePlayer&) = delete;
+    AudioFilePlayer& operator= (const AudioFilePlayer&) = delete;
+
+    void setupAudioCallback (AudioDeviceManager& deviceManager) { manager = &deviceManager; }           // :29-33
+
+    void loadFileIntoTransport (const String& audioFile)                                              // :41-60
+    {
+        playing = false; position = 0;
+        currentAudioFileSource = AudioFormatReader::createReaderFor (audioFile);
+    }
+    void play()    { playing = true; }                                                                  // :62
+    void pause()   { playing = false; }                                                                 // :63
+    void stop()    { pause(); position = 0; }                                                           // :64
+    void restart() { position = 0; }                                                                    // :65
+    bool hasFile() const { return currentAudioFileSource != nullptr; }                                  // :67
+    bool isPlaying() const noexcept { return playing; }
+    const AudioFormatReader* getReader() const noexcept { return currentAudioFileSource.get(); }
+    void setPosition (long sampleFrame) { position = sampleFrame < 0 ? 0 : sampleFrame; }
+
+    // Analyse the loaded file from the transport position to its end (complete hops only) on the manager's engine.
+    // smoothed receives [tracks][frames][12] in AudioFeatures order; returns the number of frames per track, -1 on error.
+    long analyseLoadedFile (std::vector<float>& smoothed, std::vector<float>* raw = nullptr)
+    {
+        if (! manager || ! currentAudioFileSource) return -1;
+        const AudioFormatReader& r = *currentAudioFileSource;
+        fx_engine* e = manager->getEngine();
+        const long remaining = r.lengthInSamples - position;
+        if (remaining <= 0) return 0;
+        const size_t frameBytes = (size_t) r.numChannels * (size_t) fx_pcm_bytes_per_sample (r.pcmFormat);
+        const int T = manager->getNumInputChannels();
+        const long hop = manager->getHopSize();
+        const long frames = remaining / hop;
+        smoothed.assign ((size_t) T * (size_t) frames * FX_NUM_FEATURES, 0.0f);
+        if (raw) raw->assign (smoothed.size(), 0.0f);
+        if (frames == 0) return 0;
+        long got = 0;
+        const fx_status st = fx_analyse_host_pcm (e, r.data() + (size_t) position * frameBytes, r.pcmFormat, r.numChannels, -1, 0, remaining,
+                                                  raw ? raw->data() : nullptr, smoothed.data(), nullptr, &got);
+        if (st != FX_OK || got != frames) return -1;
+        position += frames * hop;
+        return frames;
+    }
+
+private:
+    AudioDeviceManager* manager = nullptr;
+    std::unique_ptr<AudioFormatReader> currentAudioFileSource;
+    bool playing = false;
+    long position = 0;
 };
 
 // ------------------------------------------------------------------------------------------------------

@@ -130,7 +130,9 @@ enum {
 };
 int         fx_pcm_bytes_per_sample (int format);        /* 0 for an unknown format */
 /* pcm holds n_tracks rows, track_stride_bytes apart; each row is n_samples sample frames of n_channels interleaved
- * samples, of which `channel` is analysed.  Otherwise as fx_analyse_host (HOST pointers, pipelined copies, state carries
+ * samples, of which `channel` is analysed.  channel = -1: track t analyses channel t % n_channels (the reference's
+ * tracks each pick one channel of the same device stream); track_stride_bytes = 0: every track reads the same row (one
+ * multichannel file feeding all tracks).  Otherwise as fx_analyse_host (HOST pointers, pipelined copies, state carries
  * over).  fx_decode_pcm_device is the conversion alone on DEVICE pointers, asynchronous on `stream`. */
 fx_status   fx_analyse_host_pcm  (fx_engine* e, const void* pcm, int format, int n_channels, int channel,
                                   long track_stride_bytes, long n_samples,
