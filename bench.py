@@ -58,7 +58,8 @@ def emit(line: dict):
 
 def config_dict(args, n_gpus):
     return {
-        "workload": "BASELINE configs[2]: 4096-track batch, 4096-pt frames, hop 1024, 48 kHz, all 12 features per frame",
+        "workload": ("BASELINE configs[2]: 4096-track batch, 4096-pt frames, hop 1024, 48 kHz, all 12 features per frame"
+                     if (WINDOW, HOP) == (4096, 1024) else f"exploration: {WINDOW}-pt frames, hop {HOP}, 48 kHz, all 12 features per frame"),
         "tracks_per_gpu": args.tracks, "tracks_total": args.tracks * n_gpus, "seconds_per_track": args.seconds,
         "window": WINDOW, "hop": HOP, "sample_rate": SR, "frames_per_track": int(SR * args.seconds) // HOP,
         "parallelism": f"track-range sharding x{n_gpus}, no collective",
@@ -113,7 +114,7 @@ class ClockSampler:
 def measured_traffic(args):
     """DRAM bytes per k_analyse launch from the committed ncu --set full capture (only valid for the default workload)."""
     p = os.path.join(ROOT, "profiles", "k_analyse_traffic.json")
-    if args.tracks == 4096 and args.seconds == 10.0 and os.path.exists(p):
+    if args.tracks == 4096 and args.seconds == 10.0 and (WINDOW, HOP) == (4096, 1024) and os.path.exists(p):
         try:
             return float(json.load(open(p))["dram_bytes_per_launch"])
         except Exception:
@@ -191,7 +192,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcm", action="store_true", help="skip the 16-bit PCM end-to-end leg")
+    ap.add_argument("--window", type=int, default=4096, help="exploration only: the headline workload is 4096 / 1024")
+    ap.add_argument("--hop", type=int, default=1024)
     args = ap.parse_args()
+    global WINDOW, HOP
+    WINDOW, HOP = args.window, args.hop
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,12 +351,12 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, world),
             "e2e": e2e, "e2e_pcm16": e2e_pcm, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "k_analyse<16>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp32", "kernel": f"k_analyse<{WINDOW // 256}>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": traffic,
                          "peak_source": "FMA microbenchmark on this GPU (fx_measure_fp32_peak), measured",
                          "note": "binding roofline per north_star: min (HBM_BW / B, FP32_peak / F) is the FP32 term for this path",
                          "kernel_ms": k1_s * 1e3, "kernel_share_of_step": ms_k1 / ms_total if ms_total else None},
-            "roofline_hbm": {"bound": "hbm", "kernel": "k_analyse<16>", "achieved": byts / k1_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "roofline_hbm": {"bound": "hbm", "kernel": f"k_analyse<{WINDOW // 256}>", "achieved": byts / k1_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": byts / k1_s / 1e9 / hbm_peak, "traffic": traffic, "algorithmic_bytes": byts, "peak_source": hbm_src},
             "cpu_baseline": cpu,
         }
