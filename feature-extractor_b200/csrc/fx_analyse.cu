@@ -112,6 +112,13 @@ __device__ __forceinline__ float rcp_approx (float x)
     asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// a / b given rb = RN (1 / b): q0 = a rb, exact residual a - q0 b, one correction.  Exact whenever a / b is representable
+// (integer frequency ratios: the floor tests of the inharmonicity measure), correctly rounded otherwise up to rare ties.
+__device__ __forceinline__ double div_by (double a, double b, double rb)
+{
+    const double q = a * rb;
+    return fma (fma (-q, b, a), rb, q);
+}
 __device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
 {
     return (m * 2.0) * __hiloint2double ((e - 1 + 1023) << 20, 0);
@@ -221,20 +228,20 @@ extern __shared__ __align__ (128) unsigned char fx_smem_raw[];
 
 struct V16 { float2 v[16]; };
 
-// The one copy of the FFT: stage 1 (+ twiddle) -> exchange -> stage 2 (+ twiddle) -> exchange -> stage 3.
-// v: slot q * R1 + n1 = input n1 of stage-1 butterfly m0 + T q.  Returns slot s = X[klow (t) + T * out_index<16> (s)].
-// The caller guarantees the exchange buffer is free on entry; on return other threads may still be reading it.
+// The one copy of the FFT: stage 1 (+ twiddle) -> block barrier -> stage 2 (+ twiddle) -> warp barrier -> stage 3, every
+// stage in place.  v: slot q * R1 + n1 = input n1 of stage-1 butterfly m0 + T q.  The spectrum is left in the exchange
+// buffer at zpos (k); the caller puts a block barrier between this call and the first read of another thread's bins, and
+// guarantees that nobody still reads the buffer on entry (other than this thread's own stage-1 inputs).
 template <int R1>
-__device__ __noinline__ V16 fft_core (V16 io, int m0)
+__device__ __noinline__ void fft_core (V16 io, int m0)
 {
     Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
     const int t = threadIdx.x;
     fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1);
     __syncthreads();
     fft_stage2<R1, false> (t, sm.ex, sm.tw2);
-    __syncthreads();
-    fft_stage3<R1, false> (t, sm.ex, io.v);
-    return io;
+    __syncwarp();                                           // rows are private to a half warp from here on
+    fft_stage3<R1, false> (t, sm.ex);
 }
 
 template <int R1>
@@ -315,6 +322,10 @@ k_analyse (const AnalyseParams p)
     const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
     const int b0 = 8 * t;                                           // this thread's 8 consecutive bins
     const double inv_m = 1.0 / (double) M;                          // exact: M is a power of two
+    // where this thread's runs of the spectrum live in the exchange buffer (fx_fft.cuh: zpos): its 8 bins b0 + j and their
+    // mirrors N - b0 - j (j = 0 pairs with (N - b0) & (N - 1), j >= 1 with the run that starts at N - b0 - 8), and its 16 lags
+    const int zb_own = zpos<R1> (b0), zb_self = zpos<R1> ((N - b0) & (N - 1)), zb_mirror = zpos<R1> (N - b0 - 8);
+    const int zl_own = zpos<R1> (16 * t), zl_self = zpos<R1> ((N - 16 * t) & (N - 1)), zl_mirror = zpos<R1> (N - 16 * t - 16);
     // the same ramp over this thread's 16 consecutive samples (filter / pitch layout): w = wseg_0 + j wseg_d
     const float wseg_0 = (16 * t < M) ? (float) (16 * t) * (2.0f / N) : 1.0f - (float) (16 * t - M) * (2.0f / N);
     const float wseg_d = (16 * t < M) ? (2.0f / N) : -(2.0f / N);
@@ -390,7 +401,7 @@ k_analyse (const AnalyseParams p)
                 // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
                 // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
                 const float w = fmaf ((float) j, wseg_d, wseg_0);
-                sm.ex[17 * t + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));   // phys (16 t + j)
+                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));   // tpos (16 t + j)
             }
         }
         __syncthreads();
@@ -403,17 +414,11 @@ k_analyse (const AnalyseParams p)
         for (int q = 0; q < Q1; ++q)
             #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1)
-                io.v[q * R1 + n1] = sm.ex[phys (n1 * 256 + T * q + t)];
-        // no barrier: stage 1 is in place per thread (it stores to ex[k1 * ROW + phys (m)], exactly the 16 slots
-        // ex[phys (n1 * 256 + m)] = ex[n1 * ROW + phys (m)] this thread has just read)
-        io = fft_core<R1> (io, t);
-        __syncthreads();                                            // every stage-3 read is done: store Z in natural order
-        {
-            const int kl = klow<R1> (t);
-            #pragma unroll
-            for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = io.v[s];
-        }
-        __syncthreads();
+                io.v[q * R1 + n1] = sm.ex[n1 * D::ROW + phys (T * q + t)];                  // tpos (n1 * 256 + m)
+        // no barrier: stage 1 is in place per thread (it stores to ex[k1 * ROW + phys (m)], exactly the slots
+        // ex[n1 * ROW + phys (m)] this thread has just read)
+        fft_core<R1> (io, t);
+        __syncthreads();                                            // Z[k] = B[k] + i C[k] is complete, at zpos (k)
 
         // previous non-silent spectrum of this thread's bins: issued now, consumed in pass 1 (L2 latency hidden by the split)
         float4 p0 = make_float4 (0.0f, 0.0f, 0.0f, 0.0f), p1 = p0;
@@ -434,9 +439,8 @@ k_analyse (const AnalyseParams p)
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
-                const int k = b0 + j;
-                const float2 zk = sm.ex[phys (k)];
-                const float2 zn = sm.ex[phys ((N - k) & (N - 1))];
+                const float2 zk = sm.ex[zb_own + zrun<R1> (j)];                                // Z[k], k = b0 + j
+                const float2 zn = sm.ex[j == 0 ? zb_self : zb_mirror + zrun<R1> (8 - j)];      // Z[(N - k) & (N - 1)]
                 const float reB = 0.5f * (zk.x + zn.x);
                 const float imB = 0.5f * (zk.y - zn.y);
                 const float reC = 0.5f * (zk.y + zn.y);
@@ -447,7 +451,7 @@ k_analyse (const AnalyseParams p)
             }
             *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (pq[0], pq[1], pq[2], pq[3]);
             *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (pq[4], pq[5], pq[6], pq[7]);
-            if (t == 0) { const float cm = sm.ex[phys (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
+            if (t == 0) { const float cm = sm.ex[zpos<R1> (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
         }
 
         // RMS (RealTimeAnalyser.h:207-208)
@@ -570,7 +574,7 @@ k_analyse (const AnalyseParams p)
         // (same expression as the split: bit-identical); only the rare sequential paths below use it
         auto reb_at = [&] (int k) -> double
         {
-            return (double) (0.5f * (sm.ex[phys (k)].x + sm.ex[phys ((N - k) & (N - 1))].x));
+            return (double) (0.5f * (sm.ex[zpos<R1> (k)].x + sm.ex[zpos<R1> ((N - k) & (N - 1))].x));
         };
         {
             double var = 0.0, sie = 0.0, evar = 0.0;
@@ -587,60 +591,46 @@ k_analyse (const AnalyseParams p)
                 const double de = e - mean_e;                                                     // :182-190
                 evar += de * de;
             }
-            // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is
-            // still in range and the exponent budget of its bins reaches a limit.  Every thread that sees such an event
-            // replays the reference's sequential IEEE multiply (gradual underflow included, :92) from its event bin; the
-            // earliest event of the CTA (smallest code) is the one the reference's running product meets first, and
-            // thread 0 picks that thread's product when it writes the record.  Later events are speculative work that
-            // only arises when the extended-range product wanders back into range (rare).
+            // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is still in
+            // range and the exponent budget of its bins reaches a limit.  Such a thread runs the reference's own sequential IEEE
+            // multiply (:92) over its 8 bins, from registers, starting at its prefix (which equals the reference's running
+            // product up to rounding as long as no earlier thread saw an event).  If the product really left the normal range
+            // (entered the denormal band, reached 0 or inf) the thread keeps multiplying through the rest of the spectrum --
+            // gradual underflow, sticky 0 / inf and a recovery from the denormal band come out exactly as in the reference --
+            // and offers its product; thread 0 takes the offer of the earliest such thread when it writes the record.
             unsigned ev_code = 0xffffffffu;
             double ev_prod = 0.0;
             if (prefix.e < 1025 && prefix.e > -1022 && (prefix.e + e_budget >= 1025 || prefix.e - e_budget <= -1022))
             {
-                ME run = prefix;
-                #pragma unroll 1
+                double prod = ldexp_normal (prefix.m, prefix.e);
+                bool left = false;
+                #pragma unroll
                 for (int j = 0; j < 8; ++j)
                 {
-                    const double re = reb_at (b0 + j);
-                    const double mg = re * re;
+                    const double mg = (double) cr[j] * (double) cr[j];
                     if (mg > eps)
                     {
-                        const ME nxt = me_mul (run, me_from (mg));
-                        if (nxt.e >= 1025 || nxt.e <= -1022)
-                        {
-                            ev_code = (unsigned) (b0 + j) * 2u + (nxt.e >= 1025 ? 1u : 0u);
-                            break;
-                        }
-                        run = nxt;
+                        prod *= mg;
+                        const int ef = (__double2hiint (prod) >> 20) & 0x7ff;             // 0: zero / denormal, 0x7ff: inf
+                        left = left || ef == 0 || ef == 0x7ff;
                     }
                 }
-                if (ev_code != 0xffffffffu)
+                if (left)
                 {
-                    if (ev_code & 1u) ev_prod = INFINITY;
-                    else
+                    // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group of 4
+                    #pragma unroll 1
+                    for (int b = b0 + 8; b < M && prod != 0.0 && ! isinf (prod); b += 4)
                     {
-                        ev_prod = ldexp_normal (run.m, run.e);
-                        int b = (int) (ev_code >> 1);
-                        #pragma unroll 1
-                        for (; (b & 3) != 0; ++b)
+                        #pragma unroll
+                        for (int u = 0; u < 4; ++u)
                         {
-                            const double re = reb_at (b);
+                            const double re = reb_at (b + u);
                             const double mg = re * re;
-                            if (mg > eps) ev_prod *= mg;
-                        }
-                        // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group
-                        #pragma unroll 1
-                        for (; b < M && ev_prod != 0.0 && ! isinf (ev_prod); b += 4)
-                        {
-                            #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                            {
-                                const double re = reb_at (b + u);
-                                const double mg = re * re;
-                                if (mg > eps) ev_prod *= mg;
-                            }
+                            if (mg > eps) prod *= mg;
                         }
                     }
+                    ev_code = (unsigned) t;
+                    ev_prod = prod;
                 }
             }
             double s4[4] = { var, sie, flat_sum_thread, evar };
@@ -648,7 +638,7 @@ k_analyse (const AnalyseParams p)
             const unsigned wev = warp_minu (ev_code);
             if (lane < 4) sm.red[0][1 + warp_sum_slot<4> (lane)][warp] = s4[0];                   // slots 1..4: var, sie, flat_sum, evar
             if (lane == 0) sm.ucodes[0][warp] = wev;
-            if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // codes are unique: one lane
+            if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // the warp's earliest event thread
         }
         if (t == 0)
         {
@@ -719,13 +709,7 @@ k_analyse (const AnalyseParams p)
                 if (t == 0) mbar_arrive (&sm.mbar);
             }
         }
-        io = fft_core<R1> (io, t);
-        __syncthreads();
-        {
-            const int kl = klow<R1> (t);
-            #pragma unroll
-            for (int s = 0; s < 16; ++s) sm.ex[phys (kl + T * out_index<16> (s))] = io.v[s];
-        }
+        fft_core<R1> (io, t);
         // spectral record (the pass-2 partials and replayed products were published by the barrier before the transform; none of
         // the slots read here is written again before the next frame's passes)
         if (t == 0)
@@ -769,8 +753,7 @@ k_analyse (const AnalyseParams p)
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                const int s = 16 * t + j;
-                const float d = sm.ex[phys (s)].y + sm.ex[phys ((N - s) & (N - 1))].y;            // 2 * 2^k * D[s]
+                const float d = sm.ex[zl_own + zrun<R1> (j)].y + sm.ex[j == 0 ? zl_self : zl_mirror + zrun<R1> (16 - j)].y;     // Z[s] + Z[N - s]: 2 * 2^k * D[s]
                 dv[j] = d;
                 av[j] = __fmul_rn (__fmul_rn (d, d), s0f + (float) j);                            // s = 0 contributes 0
                 runf += av[j];
@@ -779,7 +762,7 @@ k_analyse (const AnalyseParams p)
             {
                 float ra[8];
                 #pragma unroll
-                for (int j = 0; j < 8; ++j) ra[j] = sm.ex[phys (b0 + j)].x;
+                for (int j = 0; j < 8; ++j) ra[j] = sm.ex[zb_own + zrun<R1> (j)].x;
                 *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (ra[0], ra[1], ra[2], ra[3]);
                 *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (ra[4], ra[5], ra[6], ra[7]);
             }
@@ -928,7 +911,8 @@ k_analyse (const AnalyseParams p)
         // f0 = sample rate / lag and the bins derived from it come from tables built on the host with the reference's own
         // double arithmetic (PitchAnalyser.h:57, HarmonicCharacteristics.h:158-185,246-249): slot 0 stands for lag -1
         const int lag_slot = lag_i < 0 ? 0 : lag_i;
-        const double f0 = __ldg (&p.f0_tab[lag_slot]);
+        const double2 f0_pair = __ldg (reinterpret_cast<const double2*> (p.f0_tab) + lag_slot);      // { f0, 1 / f0 }
+        const double f0 = f0_pair.x, inv_f0 = f0_pair.y;
         const short* htab = p.her_tab + (size_t) lag_slot * FX_HER_TAB_STRIDE;
         const int f0_bin = (int) __ldg (&htab[18]);
         int her_bin = -1;
@@ -985,8 +969,10 @@ k_analyse (const AnalyseParams p)
                     double start_f = (double) bin * frpb;                                         // :223
                     if (start_f == 0.0) start_f = frpb * 0.5;
                     const double end_f = (double) (bin + 1) * frpb;
-                    const double ra = (start_f == f0) ? 1.0 : fmax (start_f, f0) / fmin (start_f, f0);   // :251-259
-                    const double rb = (end_f == f0) ? 1.0 : fmax (end_f, f0) / fmin (end_f, f0);
+                    // :251-259 higher / lower.  Above f0 (almost every peak) the divisor is f0, whose reciprocal comes from the
+                    // per-lag table: quotient, exact residual, one correction -- the correctly rounded quotient in 3 FMAs
+                    const double ra = (start_f == f0) ? 1.0 : (start_f > f0 ? div_by (start_f, f0, inv_f0) : f0 / start_f);
+                    const double rb = (end_f == f0) ? 1.0 : (end_f > f0 ? div_by (end_f, f0, inv_f0) : f0 / end_f);
                     if (floor (ra) == floor (rb))                                                 // :232
                     {
                         const double ratio = ra < rb ? ra : rb;

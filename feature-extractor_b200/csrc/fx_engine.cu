@@ -138,14 +138,15 @@ void build_lag_tables (int N, double sample_rate, std::vector<double>& f0_tab, s
     const int M = N / 2;
     const double nyquist = sample_rate / 2.0;
     const double frpb = nyquist / (double) M;                       // HarmonicCharacteristics.h:53
-    f0_tab.assign ((size_t) N + 1, 0.0);
+    f0_tab.assign (2 * ((size_t) N + 1), 0.0);                    // { f0, 1 / f0 } per slot
     her_tab.assign ((size_t) (N + 1) * FX_HER_TAB_STRIDE, (short) -1);
     auto clamp_short = [] (double v) { return (short) (v > 32767.0 ? 32767.0 : (v < -32768.0 ? -32768.0 : v)); };
     for (int slot = 0; slot <= N; ++slot)
     {
         const double lag = slot == 0 ? -1.0 : (double) slot;
         const double f0 = (nyquist * 2.0) / lag;                    // PitchAnalyser.h:57
-        f0_tab[(size_t) slot] = f0;
+        f0_tab[2 * (size_t) slot] = f0;
+        f0_tab[2 * (size_t) slot + 1] = 1.0 / f0;
         short* row = her_tab.data() + (size_t) slot * FX_HER_TAB_STRIDE;
         const double f0_bin_d = floor (f0 / frpb);                  // :246-249
         row[18] = clamp_short (f0_bin_d);

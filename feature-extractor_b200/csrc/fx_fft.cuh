@@ -8,9 +8,13 @@
 //   n = n1 * 256 + m            (m = n2 * 16 + n3)        k = k1 + R1 * k2 + 16 * R1 * k3
 //   stage 1: butterfly m   : R1-point DFT over n1, twiddle W_N^(m k1)     -> ex[k1][m]
 //   stage 2: (k1, n3)      : 16-point DFT over n2, twiddle W_256^(n3 k2)  -> ex[k1][k2][n3]   (in place)
-//   stage 3: (k1, k2)      : 16-point DFT over n3                         -> X[k]  in registers
-// The exchange buffer is addressed with a 17/16 skew (phys (a) = a + (a >> 4)) so that the row accesses
-// of stage 2, the column accesses of stage 3 and the stride-R1 natural-order store are all conflict free.
+//   stage 3: (k1, k2)      : 16-point DFT over n3                         -> ex[k1][k2][k3]   (in place)
+// Every stage is in place per thread, and the 16 threads that share a row k1 in stages 2 and 3 are one half warp, so the
+// only block-wide barrier inside a transform is the one between stage 1 and stage 2; the 2 -> 3 exchange needs a
+// __syncwarp.  The spectrum is left in "digit order": X[k], k = k1 + R1 k2 + 16 R1 k3, lives at zpos (k) =
+// k1 * ROW + 17 k2 + k3, and the time samples a transform starts from at tpos (n) = (n >> 8) * ROW + phys (n & 255).
+// Rows are 273 elements apart and 16-element groups inside a row are skewed by one (phys (a) = a + (a >> 4)): the row
+// accesses of stage 2, the column accesses of stage 3 and the readers of runs of consecutive bins are conflict free.
 // Twiddles come from small tables evaluated in double on the host and rounded to fp32 (as JUCE does); the stage-1
 // twiddle W_N^(m k1) is the product of two table entries, W_N^(16 mh k1) * W_N^(ml k1) with m = 16 mh + ml, which
 // keeps the tables at a few KB so that three CTAs fit on an SM.
@@ -117,19 +121,12 @@ template <int R1> struct FftDims
     static constexpr int N       = R1 * 256;
     static constexpr int T       = R1 * 16;            // threads
     static constexpr int Q1      = 16 / R1;            // stage-1 butterflies per thread
-    static constexpr int ROW     = 272;                // 256 * 17 / 16
-    static constexpr int EX_LEN  = R1 * ROW;           // float2 elements in the exchange buffer (= N * 17 / 16)
+    static constexpr int ROW     = 273;                // 256 * 17 / 16 + 1: consecutive bins (consecutive k1) fall into different banks
+    static constexpr int EX_LEN  = R1 * ROW;           // float2 elements in the exchange buffer
     static constexpr int TW1_LEN = (R1 - 1) * 32;      // float2, tw1[(k1 - 1) * 32 + mh]      = W_N^(16 mh k1)   (mh < 16)
                                                        //         tw1[(k1 - 1) * 32 + 16 + ml] = W_N^(ml k1)      (ml < 16)
     static constexpr int TW2_LEN = 15 * 16;            // float2, tw2[(k2 - 1) * 16 + n3]      = W_256^(n3 k2)
 };
-
-// butterfly index of stage 1 that thread t handles in its q-th slot group
-//   natural:  m = t + T q                      (inputs gathered from memory)
-//   chained:  m = klow (t) + T q, klow (t) = (t >> 4) + R1 (t & 15)
-//             (inputs are the registers left by stage 3 of a previous transform: thread t holds
-//              X[klow (t) + T k3], which is exactly input n1 of butterfly q when k3 = q + Q1 n1)
-template <int R1> __device__ __forceinline__ int klow (int t) { return (t >> 4) + R1 * (t & 15); }
 
 // Stage 1 on v (slot q * R1 + n1 = input n1 of butterfly q), then twiddle and store to ex.
 template <int R1, bool INV>
@@ -180,29 +177,37 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     }
 }
 
-// Stage 3: afterwards slot s of v holds X[klow (t) + T * out_index<16> (s)].
+// Stage 3 in place: X[k1 + R1 k2 + 16 R1 k3] replaces element (k2, n3 = k3) of row k1.  The caller has made the stage-2
+// stores of this half warp visible (__syncwarp).
 template <int R1, bool INV>
-__device__ __forceinline__ void fft_stage3 (int t, const float2* __restrict__ ex, float2* v)
+__device__ __forceinline__ void fft_stage3 (int t, float2* __restrict__ ex)
 {
     using D = FftDims<R1>;
     const int k1 = t >> 4, k2 = t & 15;
-    const float2* col = ex + k1 * D::ROW + k2 * 17;
+    float2* col = ex + k1 * D::ROW + k2 * 17;
+    float2 v[16];
     #pragma unroll
     for (int n3 = 0; n3 < 16; ++n3) v[n3] = col[n3];
     butterfly<16, INV> (v);
+    __syncwarp();                                         // every thread of the row has read its column
+    #pragma unroll
+    for (int s = 0; s < 16; ++s) col[out_index<16> (s)] = v[s];
 }
 
-// Re-order the registers left by fft_stage3 into the stage-1 input order of a chained transform:
-// out[q * R1 + n1] = X[klow + T (q + Q1 n1)].
-template <int R1>
-__device__ __forceinline__ void chain_permute (const float2* v3, float2* v1)
+// position of spectrum bin k / of time sample n in the exchange buffer (see the header comment)
+template <int R1> __device__ __forceinline__ int zpos (int k)
 {
     using D = FftDims<R1>;
-    #pragma unroll
-    for (int q = 0; q < D::Q1; ++q)
-        #pragma unroll
-        for (int n1 = 0; n1 < R1; ++n1)
-            v1[q * R1 + n1] = v3[slot_of<16> (q + D::Q1 * n1)];
+    return (k & (R1 - 1)) * D::ROW + ((k / R1) & 15) * 17 + k / (16 * R1);
+}
+template <int R1> __device__ __forceinline__ int tpos (int n)
+{
+    return (n >> 8) * FftDims<R1>::ROW + phys (n & 255);
+}
+// zpos (b + j) - zpos (b) for a run of bins that starts at a multiple of 8 (j < 8) or of 16 (j < 16): a compile-time offset
+template <int R1> __device__ __forceinline__ constexpr int zrun (int j)
+{
+    return (j & (R1 - 1)) * FftDims<R1>::ROW + (j / R1) * 17;
 }
 
 } // namespace fx

@@ -42,7 +42,7 @@ struct AnalyseParams
     const float2* tw1;             // global twiddle tables (fx_fft.cuh layout)
     const float2* tw2;
     // per-lag tables, slot lag = 1 .. window, slot 0 = "no lag found" (lag -1), evaluated on the host in the reference's own
-    // double arithmetic:  f0_tab[lag] = (nyquist * 2) / lag  (PitchAnalyser.h:57)
+    // double arithmetic:  f0_tab[2 lag] = (nyquist * 2) / lag  (PitchAnalyser.h:57), f0_tab[2 lag + 1] = its reciprocal
     // her_tab[lag][0..14] = bin of the sub-octave f0 / 2^(l+1), [15..17] = bin of the harmonic h f0, h = 1..3, or -1 when the
     // reference does not use it (HarmonicCharacteristics.h:158-185); [18] = bin of f0 itself (:246-249), clamped to a short
     const double* f0_tab;
