@@ -222,6 +222,7 @@ template <int R1> struct Smem
     double   ev_prod[NW];           // flatness product replayed by the warp's earliest range event
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     uint64_t mbar;
+    const float2* tw1f;
 };
 
 extern __shared__ __align__ (128) unsigned char fx_smem_raw[];
@@ -237,7 +238,7 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
 {
     Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
     const int t = threadIdx.x;
-    fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1);
+    fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1, sm.tw1f);
     __syncthreads();
     fft_stage2<R1, false> (t, sm.ex, sm.tw2);
     __syncwarp();                                           // rows are private to a half warp from here on
@@ -275,9 +276,9 @@ k_analyse (const AnalyseParams p)
     const float* src = p.audio + track * p.track_stride;
     const float* tail = p.tail_in + track * (long) (N - H);
 
-    for (int i = t; i < D::TW1_LEN; i += T) sm.tw1[i] = p.tw1[i];
+    if (! FX_TW1_GLOBAL) for (int i = t; i < D::TW1_LEN; i += T) sm.tw1[i] = p.tw1[i];
     for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[i];
-    if (t == 0) { mbar_init (&sm.mbar, 1); }
+    if (t == 0) { mbar_init (&sm.mbar, 1); sm.tw1f = p.tw1f; }
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 

@@ -36,7 +36,7 @@ struct fx_engine
     std::string err;
     std::atomic<uint64_t> launches{0};
 
-    float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw1f = nullptr;
     double *d_f0_tab = nullptr;
     short  *d_her_tab = nullptr;
     double bin_var = 0.0;
@@ -110,7 +110,7 @@ bool fail (fx_engine* e, fx_status&, const char* what, cudaError_t ce)
 int ilog2 (int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // twiddle tables in the layout fx_fft.cuh expects; evaluated in double, rounded to fp32 (as juce::FFT does)
-void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2)
+void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2, std::vector<float2>& tw1f)
 {
     const int R1 = N / 256;
     const double pi = 3.14159265358979323846;
@@ -122,6 +122,16 @@ void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2)
             const double pb = -2.0 * pi * (double) (i * k1) / (double) N;                      // W_N^(ml k1)
             tw1[(size_t) (k1 - 1) * 32 + i]      = make_float2 ((float) cos (pa), (float) sin (pa));
             tw1[(size_t) (k1 - 1) * 32 + 16 + i] = make_float2 ((float) cos (pb), (float) sin (pb));
+        }
+    // the full stage-1 table: W_N^(m k1) = W_N^(16 mh k1) * W_N^(ml k1), m = 16 mh + ml, as the fp32 product of the two
+    // factors above with the roundings of the kernel's former in-line product (one rounded product, one FMA per part)
+    tw1f.assign ((size_t) (R1 - 1) * 256, make_float2 (1.0f, 0.0f));
+    for (int k1 = 1; k1 < R1; ++k1)
+        for (int m = 0; m < 256; ++m)
+        {
+            const float2 wa = tw1[(size_t) (k1 - 1) * 32 + (m >> 4)], wb = tw1[(size_t) (k1 - 1) * 32 + 16 + (m & 15)];
+            volatile float pyy = wa.y * wb.y, pxy = wa.x * wb.y;
+            tw1f[(size_t) (k1 - 1) * 256 + m] = make_float2 (fmaf (wa.x, wb.x, -pyy), fmaf (wa.y, wb.x, pxy));
         }
     tw2.assign (15 * 16, make_float2 (1.0f, 0.0f));
     for (int k2 = 1; k2 < 16; ++k2)
@@ -263,7 +273,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.use_bulk = (((uintptr_t) d_audio & 15u) == 0 && (track_stride % 4) == 0 && (e->H % 4) == 0) ? 1 : 0;
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
-    a.tw1 = e->d_tw1; a.tw2 = e->d_tw2;
+    a.tw1 = e->d_tw1; a.tw2 = e->d_tw2; a.tw1f = e->d_tw1f;
     a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab;
     a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
@@ -312,7 +322,7 @@ void free_engine (fx_engine* e)
     if (! e) return;
     cudaSetDevice (e->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab);
+    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_tw1f); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab);
     cudaFree (e->d_gain); cudaFree (e->d_mult); cudaFree (e->d_type); cudaFree (e->d_hist); cudaFree (e->d_reset);
     for (int i = 0; i < 2; ++i) { cudaFree (e->d_tail[i]); cudaFree (e->d_prev[i]); cudaFree (e->d_hrows[i]); }
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
@@ -397,12 +407,14 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
     FX_CREATE (configure_analyse (N));
     FX_CREATE (cudaStreamCreateWithFlags (&e->stream, cudaStreamNonBlocking));
 
-    std::vector<float2> tw1, tw2;
-    build_twiddles (N, tw1, tw2);
+    std::vector<float2> tw1, tw2, tw1f;
+    build_twiddles (N, tw1, tw2, tw1f);
     FX_CREATE (cudaMalloc (&e->d_tw1, tw1.size() * sizeof (float2)));
     FX_CREATE (cudaMalloc (&e->d_tw2, tw2.size() * sizeof (float2)));
     FX_CREATE (cudaMemcpy (e->d_tw1, tw1.data(), tw1.size() * sizeof (float2), cudaMemcpyHostToDevice));
     FX_CREATE (cudaMemcpy (e->d_tw2, tw2.data(), tw2.size() * sizeof (float2), cudaMemcpyHostToDevice));
+    FX_CREATE (cudaMalloc (&e->d_tw1f, tw1f.size() * sizeof (float2)));
+    FX_CREATE (cudaMemcpy (e->d_tw1f, tw1f.data(), tw1f.size() * sizeof (float2), cudaMemcpyHostToDevice));
     {
         std::vector<double> f0_tab; std::vector<short> her_tab;
         build_lag_tables (N, cfg->sample_rate, f0_tab, her_tab);

@@ -21,6 +21,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef FX_TW1_GLOBAL
+#define FX_TW1_GLOBAL 1     // 1: stage-1 twiddles from the full global table through L1 (one 8-byte load per twiddle, measured
+                            //    1.7 % faster); 0: product of two small shared-memory factors (two loads and a complex multiply)
+#endif
+
 namespace fx {
 
 __device__ __forceinline__ int phys (int a) { return a + (a >> 4); }
@@ -130,7 +135,7 @@ template <int R1> struct FftDims
 
 // Stage 1 on v (slot q * R1 + n1 = input n1 of butterfly q), then twiddle and store to ex.
 template <int R1, bool INV>
-__device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __restrict__ ex, const float2* __restrict__ tw1)
+__device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __restrict__ ex, const float2* __restrict__ tw1, const float2* __restrict__ tw1f)
 {
     using D = FftDims<R1>;
     #pragma unroll
@@ -147,8 +152,12 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
             float2 val = v[q * R1 + s];
             if (k1 > 0)
             {
+#if FX_TW1_GLOBAL
+                const float2 w = __ldg (&tw1f[(k1 - 1) * 256 + m]);
+#else
                 const float2 wa = tw1[(k1 - 1) * 32 + mh], wb = tw1[(k1 - 1) * 32 + ml];
                 const float2 w = make_float2 (wa.x * wb.x - wa.y * wb.y, wa.x * wb.y + wa.y * wb.x);
+#endif
                 val = cmulw<INV> (val, w);
             }
             ex[k1 * D::ROW + pm] = val;

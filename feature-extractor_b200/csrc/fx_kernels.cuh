@@ -41,6 +41,7 @@ struct AnalyseParams
     float        iir_c1, iir_c2;   // pi/2 and exp (-pi/2) in fp32 (RealTimeAudioAnalysis.h:122)
     const float2* tw1;             // global twiddle tables (fx_fft.cuh layout)
     const float2* tw2;
+    const float2* tw1f;            // stage-1 twiddles in full, [(k1 - 1) * 256 + m] = W_N^(m k1) (the two-factor product, rounded as the kernel used to), read through L1
     // per-lag tables, slot lag = 1 .. window, slot 0 = "no lag found" (lag -1), evaluated on the host in the reference's own
     // double arithmetic:  f0_tab[2 lag] = (nyquist * 2) / lag  (PitchAnalyser.h:57), f0_tab[2 lag + 1] = its reciprocal
     // her_tab[lag][0..14] = bin of the sub-octave f0 / 2^(l+1), [15..17] = bin of the harmonic h f0, h = 1..3, or -1 when the
