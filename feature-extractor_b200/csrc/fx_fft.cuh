@@ -144,7 +144,9 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
         butterfly<R1, INV> (v + q * R1);
         const int m = m0 + D::T * q;
         const int pm = phys (m);
+#if ! FX_TW1_GLOBAL
         const int mh = m >> 4, ml = 16 + (m & 15);
+#endif
         #pragma unroll
         for (int s = 0; s < R1; ++s)
         {
