@@ -214,7 +214,7 @@ template <int R1> struct Smem
     double   pscan[NW];              // pitch cumulative sum scan, warp totals
     unsigned long long keys[NW];
     unsigned ucodes[2][NW];
-    float    fmins[2][NW];
+    float    fmins[3][NW];           // [0] flatness gate margin, [1] max |Re|, |Im| of the lower bins (slope quirk), [2] peak margin
     float    fmaxs[NW];
     float    psums[NW];
     float    pmins[2][NW];           // pitch margin / runner-up partials
@@ -571,12 +571,7 @@ k_analyse (const AnalyseParams p)
         // this one because the mean follows from pass 1's magnitude sum: sum (mag * (1 / maxE)) and magSum * (1 / maxE)
         // differ by fp64 rounding only (1e-16 relative on a feature compared at 1e-4).
         const double mean_e = (mag_sum * inv_max_e) * inv_m;
-        // Re B[k] recomputed from the packed spectrum, which stays in the exchange buffer until FFT-beta's barrier
-        // (same expression as the split: bit-identical); only the rare sequential paths below use it
-        auto reb_at = [&] (int k) -> double
-        {
-            return (double) (0.5f * (sm.ex[zpos<R1> (k)].x + sm.ex[zpos<R1> ((N - k) & (N - 1))].x));
-        };
+        // (the packed spectrum stays in the exchange buffer until FFT-beta's barrier: the flatness replay below re-reads it)
         {
             double var = 0.0, sie = 0.0, evar = 0.0;
             const double cn = (double) centroid / nyquist;                                        // :137
@@ -625,7 +620,7 @@ k_analyse (const AnalyseParams p)
                         #pragma unroll
                         for (int u = 0; u < 4; ++u)
                         {
-                            const double re = reb_at (b + u);
+                            const double re = (double) (0.5f * (sm.ex[zpos<R1> (b + u)].x + sm.ex[zpos<R1> (N - b - u)].x));
                             const double mg = re * re;
                             if (mg > eps) prod *= mg;
                         }
@@ -711,36 +706,7 @@ k_analyse (const AnalyseParams p)
             }
         }
         fft_core<R1> (io, t);
-        // spectral record (the pass-2 partials and replayed products were published by the barrier before the transform; none of
-        // the slots read here is written again before the next frame's passes)
-        if (t == 0)
-        {
-            // the pass-1 slots red[1][2..3], icount, fmins[0] and the pass-2 slots red[0][1..4], ucodes[0], ev_prod are not written again before the barrier below
-            double evar = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0, count = 0.0, var = 0.0, sie = 0.0;
-            float flat_margin = 1.0f;
-            unsigned ev = 0xffffffffu; int ev_warp = 0;
-            #pragma unroll
-            for (int w = 0; w < NW; ++w)
-            {
-                flux += sm.red[1][2][w]; lhr += sm.red[1][3][w]; count += (double) sm.icount[w];
-                var += sm.red[0][1][w]; sie += sm.red[0][2][w]; flat_sum += sm.red[0][3][w]; evar += sm.red[0][4][w];
-                flat_margin = fminf (flat_margin, sm.fmins[0][w]);
-                if (sm.ucodes[0][w] < ev) { ev = sm.ucodes[0][w]; ev_warp = w; }
-            }
-            double product; float flat_state;
-            if (ev == 0xffffffffu)
-            {
-                ME total = me_one();
-                #pragma unroll 1
-                for (int w = 0; w < NW; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; total = me_mul (total, wt); }
-                product = ldexp_normal (total.m, total.e); flat_state = 0.0f;
-            }
-            else { product = sm.ev_prod[ev_warp]; flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f); }
-            rec->flux = flux; rec->lhr = lhr;
-            rec->flat_sum = flat_sum; rec->count = count; rec->product = product; rec->var = var; rec->sie = sie;
-            rec->evar = evar;
-            rec->flat_margin = flat_margin; rec->flat_state = silent ? 3.0f : flat_state;
-        }
+        // (the record of this frame is written after the frame's last barrier, one part per warp)
         __syncthreads();
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
@@ -989,46 +955,99 @@ k_analyse (const AnalyseParams p)
             warp_sum_t<2> (s2, lane);
             const int wnp = warp_addi (npeaks);
             const float wpk = warp_min_nonneg (pkm);
-            if (lane < 2) sm.red[1][1 + warp_sum_slot<2> (lane)][warp] = s2[0];
-            if (lane == 0) { sm.ipeaks[warp] = wnp; sm.fmins[0][warp] = wpk; }
+            if (lane < 2) sm.red[1][6 + warp_sum_slot<2> (lane)][warp] = s2[0];                   // slots 6, 7: sum_normed, inharm
+            if (lane == 0) { sm.ipeaks[warp] = wnp; sm.fmins[2][warp] = wpk; }
         }
         __syncthreads();
-        // No barrier closes the frame: warp 0 finishes the harmonic record below while the other warps start the next
-        // frame's filter.  What it reads (the normalised magnitudes, the reduction slots) is not written again before the
-        // barriers of the next frame's first transform, which need warp 0.
-        if (warp == 0)
+        // ---- the frame's record (what K1b needs), one part per warp ---------------------------------------------------
+        // No barrier closes the frame.  Every per-warp partial of the frame is still in its slot (each reduction of a frame has
+        // its own slot, and none is written again before the barriers inside the next frame's first transform, which need
+        // every warp).  Lane w < NW of a warp loads warp w's partial, a butterfly over those lanes sums them, and the warp
+        // stores its fields; the five parts run on different warps, so no single warp is late for the next frame's barrier.
         {
-            // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
-            // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3 (bins from the table, -1 = not used: a sub-octave in
-            // f0's own bin is skipped (:163-164), harmonics stop at the first bin >= M (:174-175)); the sums are warp reductions
-            double term = 0.0;
-            if (her_bin >= 0 && ! hsilent)
+            constexpr int LOG_NW = NW == 8 ? 3 : (NW == 4 ? 2 : 1);
+            auto sum_nw = [&] (double v) -> double                  // sum over lanes 0 .. NW-1 (all lanes must call)
             {
-                const int st = her_bin - 2 >= 0 ? her_bin - 2 : 0;
-                const int en = her_bin + 2 < M ? her_bin + 2 : M;
-                float mx = sm.pa[her_bin];                                                        // :200-210
-                for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, sm.pa[bb]);
-                term = (double) mx;
-            }
-            // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
-            const double even = __shfl_sync (0xffffffffu, term, 16);
-            const double odd = __shfl_sync (0xffffffffu, term, 15) + __shfl_sync (0xffffffffu, term, 17);
-            double s1[1] = { term };
-            warp_sum<1> (s1);
-            if (lane == 0)
-            {
-                double sum_normed = 0.0, inharm = 0.0, npeaks = 0.0; float pkm = 1.0f, pmm = 1.0f, second = 100.0f;
                 #pragma unroll
-                for (int w = 0; w < NW; ++w)
+                for (int sft = 0; sft < LOG_NW; ++sft) v += __shfl_xor_sync (0xffffffffu, v, 1 << sft);
+                return v;
+            };
+            const bool ld = lane < NW;
+            if (warp == 0 % NW)
+            {
+                // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
+                // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3 (bins from the table, -1 = not used: a sub-octave in
+                // f0's own bin is skipped (:163-164), harmonics stop at the first bin >= M (:174-175)); the sums are warp reductions
+                double term = 0.0;
+                if (her_bin >= 0 && ! hsilent)
                 {
-                    sum_normed += sm.red[1][1][w]; inharm += sm.red[1][2][w]; npeaks += (double) sm.ipeaks[w]; pkm = fminf (pkm, sm.fmins[0][w]);
-                    pmm = fminf (pmm, sm.pmins[0][w]); second = fminf (second, sm.pmins[1][w]);
+                    const int st = her_bin - 2 >= 0 ? her_bin - 2 : 0;
+                    const int en = her_bin + 2 < M ? her_bin + 2 : M;
+                    float mx = sm.pa[her_bin];                                                    // :200-210
+                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, sm.pa[bb]);
+                    term = (double) mx;
                 }
+                // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
+                const double even = __shfl_sync (0xffffffffu, term, 16);
+                const double odd = __shfl_sync (0xffffffffu, term, 15) + __shfl_sync (0xffffffffu, term, 17);
+                double s1[1] = { term };
+                warp_sum<1> (s1);
+                if (lane == 0) { rec->score = s1[0]; rec->even = even; rec->odd = odd; }
+            }
+            if (warp == 1 % NW)
+            {
+                const double sum_normed = sum_nw (ld ? sm.red[1][6][lane] : 0.0), inharm = sum_nw (ld ? sm.red[1][7][lane] : 0.0);
+                const int npeaks = warp_addi (ld ? sm.ipeaks[lane] : 0);
+                const float pkm = warp_min_nonneg (ld ? sm.fmins[2][lane] : 1.0f);
+                float pmm = warp_min_nonneg (ld ? sm.pmins[0][lane] : 1.0f);
+                const float second = warp_min_nonneg (ld ? sm.pmins[1][lane] : 100.0f);
                 if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
-                rec->lag = (float) lag_i; rec->pitch_margin = pmm;
-                rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
-                rec->score = s1[0]; rec->even = even; rec->odd = odd;
-                rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
+                if (lane == 0)
+                {
+                    rec->lag = (float) lag_i; rec->pitch_margin = pmm;
+                    rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
+                    rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
+                }
+            }
+            if (warp == 2 % NW)
+            {
+                const double flux = sum_nw (ld ? sm.red[1][2][lane] : 0.0), lhr = sum_nw (ld ? sm.red[1][3][lane] : 0.0);
+                const double flat_sum = sum_nw (ld ? sm.red[0][3][lane] : 0.0);
+                const int count = warp_addi (ld ? sm.icount[lane] : 0);
+                if (lane == 0) { rec->flux = flux; rec->lhr = lhr; rec->flat_sum = flat_sum; rec->count = (double) count; }
+            }
+            if (warp == 3 % NW)
+            {
+                const double var = sum_nw (ld ? sm.red[0][1][lane] : 0.0), sie = sum_nw (ld ? sm.red[0][2][lane] : 0.0);
+                const double evar = sum_nw (ld ? sm.red[0][4][lane] : 0.0);
+                const float flat_margin = warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f);
+                if (lane == 0) { rec->var = var; rec->sie = sie; rec->evar = evar; rec->flat_margin = flat_margin; }
+            }
+            if (warp == 4 % NW)
+            {
+                // flatness product: the offer of the earliest event thread, else the product of the warp totals of the scan
+                const unsigned evc = ld ? sm.ucodes[0][lane] : 0xffffffffu;
+                const unsigned ev = warp_minu (evc);
+                double product; float flat_state = 0.0f;
+                if (ev == 0xffffffffu)
+                {
+                    ME tot = me_one();
+                    if (ld) { tot.m = sm.scan_m[lane]; tot.e = sm.scan_e[lane]; }
+                    #pragma unroll
+                    for (int sft = 0; sft < LOG_NW; ++sft)
+                    {
+                        ME o; o.m = __shfl_xor_sync (0xffffffffu, tot.m, 1 << sft); o.e = __shfl_xor_sync (0xffffffffu, tot.e, 1 << sft);
+                        tot = me_mul (tot, o);
+                    }
+                    product = ldexp_normal (tot.m, tot.e);
+                }
+                else
+                {
+                    const int ev_warp = __ffs ((int) __ballot_sync (0xffffffffu, evc == ev)) - 1;
+                    product = sm.ev_prod[ev_warp];
+                    flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f);
+                }
+                if (lane == 0) { rec->product = product; rec->flat_state = silent ? 3.0f : flat_state; }
             }
         }
     }
