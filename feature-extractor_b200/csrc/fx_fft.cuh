@@ -30,15 +30,60 @@ namespace fx {
 
 __device__ __forceinline__ int phys (int a) { return a + (a >> 4); }
 
-__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+// Packed fp32 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2): one instruction works on both halves of a 64-bit register
+// pair, IEEE round-to-nearest per half like the scalar forms.  A complex value is such a pair, so a complex add is one
+// instruction and a complex multiply two; ptxas folds the component swaps and negations of the operands below into
+// the instructions' operand modifiers (.LO_HI, .NP, .F32 broadcast).  The kernel is bound by issue slots, not by the
+// FP32 pipe: the packed forms halve the issue slots of the butterflies.
+#ifndef FX_F32X2
+#define FX_F32X2 1
+#endif
+#if FX_F32X2
+__device__ __forceinline__ float2 f2add (float2 a, float2 b)
+{
+    float2 r;
+    asm ("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2sub (float2 a, float2 b)
+{
+    float2 r;
+    asm ("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2mul (float2 a, float2 b)
+{
+    float2 r;
+    asm ("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2fma (float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm ("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+#else
+__device__ __forceinline__ float2 f2add (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2mul (float2 a, float2 b) { return make_float2 (__fmul_rn (a.x, b.x), __fmul_rn (a.y, b.y)); }
+__device__ __forceinline__ float2 f2fma (float2 a, float2 b, float2 c) { return make_float2 (fmaf (a.x, b.x, c.x), fmaf (a.y, b.y, c.y)); }
+#endif
 
-// a * w (forward) or a * conj (w) (inverse)
+__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return f2add (a, b); }
+__device__ __forceinline__ float2 csub (float2 a, float2 b) { return f2sub (a, b); }
+
+// a * w (forward) or a * conj (w) (inverse): (a.x w.x -+ a.y w.y, a.y w.x +- a.x w.y) as one packed multiply and one packed FMA
 template <bool INV>
 __device__ __forceinline__ float2 cmulw (float2 a, float2 w)
 {
-    if (INV) return make_float2 (a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
-    else     return make_float2 (a.x * w.x - a.y * w.y, a.y * w.x + a.x * w.y);
+    const float2 wy = make_float2 (w.y, w.y), wx = make_float2 (w.x, w.x);
+    if (INV) return f2fma (a, wx, f2mul (make_float2 (a.y, -a.x), wy));
+    else     return f2fma (a, wx, f2mul (make_float2 (-a.y, a.x), wy));
 }
 
 // multiply by -i (forward) / +i (inverse)
