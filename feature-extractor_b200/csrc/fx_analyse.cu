@@ -10,7 +10,8 @@
 //
 // Data movement: the hop's new samples arrive by cp.async.bulk (TMA bulk copy, mbarrier completion) into a
 // shared-memory ring holding the N-sample window, so each input sample crosses HBM once per chunk; the next
-// hop is prefetched while the current frame's second transform and the pitch / harmonic passes run.
+// hop is prefetched as soon as the frame's last read of the ring is behind a barrier and lands during the pitch /
+// harmonic passes.
 // The reference runs four real-input transforms per hop; here they are packed into TWO complex FFTs, both through
 // ONE out-of-line copy of the FFT code (the kernel is instruction-cache bound otherwise):
 //   FFT-alpha  z = x w + i onepole (x) w   -> B = FFT (x w): Re B (+ Im B for the slope quirk), C: P[k] = Re C[k]^2,
@@ -24,6 +25,16 @@
 #include "fx_fft.cuh"
 #include "fx_kernels.cuh"
 #include <math.h>
+
+#ifndef FX_P_FILTER
+#define FX_P_FILTER 1
+#endif
+#ifndef FX_P_GATHER
+#define FX_P_GATHER 1
+#endif
+#ifndef FX_P_SPLIT
+#define FX_P_SPLIT 0
+#endif
 
 namespace fx {
 
@@ -202,10 +213,10 @@ template <int R1> struct Smem
     static constexpr int kRed = 10;
 
     float2   ex[D::EX_LEN];          // FFT exchange buffer; doubles as two fp32 work arrays (skewed, N*17/16 floats each)
-    float2   tw1[D::TW1_LEN];
+    float2   tw1[FX_TW1_GLOBAL ? 1 : D::TW1_LEN];     // stage-1 twiddle factors (only when they are not read from the global table)
     float2   tw2[D::TW2_LEN];
-    float    ring[N];                // ring[a & (N-1)] = absolute sample a of the track
-    float    pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
+    alignas (128) float ring[N];     // ring[a & (N-1)] = absolute sample a of the track (bulk-copy destination, float4 reads)
+    alignas (16) float pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
     double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
     int      icount[NW];             // flatness gate count, warp totals
     int      ipeaks[NW];             // number of spectral peaks, warp totals
@@ -328,8 +339,10 @@ k_analyse (const AnalyseParams p)
     const int zb_own = zpos<R1> (b0), zb_self = zpos<R1> ((N - b0) & (N - 1)), zb_mirror = zpos<R1> (N - b0 - 8);
     const int zl_own = zpos<R1> (16 * t), zl_self = zpos<R1> ((N - 16 * t) & (N - 1)), zl_mirror = zpos<R1> (N - 16 * t - 16);
     // the same ramp over this thread's 16 consecutive samples (filter / pitch layout): w = wseg_0 + j wseg_d
-    const float wseg_0 = (16 * t < M) ? (float) (16 * t) * (2.0f / N) : 1.0f - (float) (16 * t - M) * (2.0f / N);
-    const float wseg_d = (16 * t < M) ? (2.0f / N) : -(2.0f / N);
+    // The ramp is stored halved: FFT-alpha then delivers Z / 2 (a power-of-two scale commutes with every rounding of the
+    // transform), and the split B = (Z[k] + conj Z[N-k]) / 2 needs no multiplications.
+    const float wseg_0 = 0.5f * ((16 * t < M) ? (float) (16 * t) * (2.0f / N) : 1.0f - (float) (16 * t - M) * (2.0f / N));
+    const float wseg_d = (16 * t < M) ? (1.0f / N) : -(1.0f / N);
 
     #pragma unroll 1
     for (int f = f_begin; f < f_end; ++f)
@@ -401,8 +414,13 @@ k_analyse (const AnalyseParams p)
                 if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
                 // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
                 // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
+                // (packed multiply: both sequences by the same ramp value.  What is stored is z / 2 -- see the split below)
                 const float w = fmaf ((float) j, wseg_d, wseg_0);
-                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));   // tpos (16 t + j)
+#if FX_P_FILTER
+                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = f2mul (make_float2 (__fmul_rn (xs[j], gain), ys[j]), make_float2 (w, w));   // tpos (16 t + j)
+#else
+                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));
+#endif
             }
         }
         __syncthreads();
@@ -429,7 +447,7 @@ k_analyse (const AnalyseParams p)
             p1 = *reinterpret_cast<const float4*> (&prev_g[b0 + 4]);
         }
         // Split for this thread's own 8 consecutive bins k: Z[k] = B[k] + i C[k], conj Z[N-k] = B[k] - i C[k]
-        //   Re B = (Zk.x + Zn.x) / 2   Im B = (Zk.y - Zn.y) / 2   Re C = (Zk.y + Zn.y) / 2
+        //   Re B = (Zk.x + Zn.x) / 2   Im B = (Zk.y - Zn.y) / 2   Re C = (Zk.y + Zn.y) / 2     (the buffer holds Z / 2)
         // Re B stays in registers for the spectral passes; P[k] = Re C[k]^2 (PitchAnalyser.h:97-104, imaginary part
         // cleared) goes to the P / Re A array as the imaginary input of FFT-beta.
         float cr[8];
@@ -442,9 +460,13 @@ k_analyse (const AnalyseParams p)
             {
                 const float2 zk = sm.ex[zb_own + zrun<R1> (j)];                                // Z[k], k = b0 + j
                 const float2 zn = sm.ex[j == 0 ? zb_self : zb_mirror + zrun<R1> (8 - j)];      // Z[(N - k) & (N - 1)]
-                const float reB = 0.5f * (zk.x + zn.x);
-                const float imB = 0.5f * (zk.y - zn.y);
-                const float reC = 0.5f * (zk.y + zn.y);
+#if FX_P_SPLIT
+                const float2 bc = f2add (zk, zn);                                               // (Re B, Re C): the 1/2 is in the window
+                const float reB = bc.x, reC = bc.y;
+#else
+                const float reB = zk.x + zn.x, reC = zk.y + zn.y;
+#endif
+                const float imB = zk.y - zn.y;
                 cr[j] = reB;
                 if (b0 < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
                 pq[j] = __fmul_rn (reC, reC);
@@ -452,7 +474,7 @@ k_analyse (const AnalyseParams p)
             }
             *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (pq[0], pq[1], pq[2], pq[3]);
             *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (pq[4], pq[5], pq[6], pq[7]);
-            if (t == 0) { const float cm = sm.ex[zpos<R1> (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
+            if (t == 0) { const float cm = 2.0f * sm.ex[zpos<R1> (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
         }
 
         // RMS (RealTimeAnalyser.h:207-208)
@@ -571,7 +593,6 @@ k_analyse (const AnalyseParams p)
         // this one because the mean follows from pass 1's magnitude sum: sum (mag * (1 / maxE)) and magSum * (1 / maxE)
         // differ by fp64 rounding only (1e-16 relative on a feature compared at 1e-4).
         const double mean_e = (mag_sum * inv_max_e) * inv_m;
-        // (the packed spectrum stays in the exchange buffer until FFT-beta's barrier: the flatness replay below re-reads it)
         {
             double var = 0.0, sie = 0.0, evar = 0.0;
             const double cn = (double) centroid / nyquist;                                        // :137
@@ -591,9 +612,9 @@ k_analyse (const AnalyseParams p)
             // range and the exponent budget of its bins reaches a limit.  Such a thread runs the reference's own sequential IEEE
             // multiply (:92) over its 8 bins, from registers, starting at its prefix (which equals the reference's running
             // product up to rounding as long as no earlier thread saw an event).  If the product really left the normal range
-            // (entered the denormal band, reached 0 or inf) the thread keeps multiplying through the rest of the spectrum --
-            // gradual underflow, sticky 0 / inf and a recovery from the denormal band come out exactly as in the reference --
-            // and offers its product; thread 0 takes the offer of the earliest such thread when it writes the record.
+            // (entered the denormal band, reached 0 or inf) the thread offers its product; the record stage takes the offer
+            // of the earliest such thread and keeps multiplying through the rest of the spectrum -- gradual underflow, sticky
+            // 0 / inf and a recovery from the denormal band come out exactly as in the reference.
             unsigned ev_code = 0xffffffffu;
             double ev_prod = 0.0;
             if (prefix.e < 1025 && prefix.e > -1022 && (prefix.e + e_budget >= 1025 || prefix.e - e_budget <= -1022))
@@ -611,23 +632,7 @@ k_analyse (const AnalyseParams p)
                         left = left || ef == 0 || ef == 0x7ff;
                     }
                 }
-                if (left)
-                {
-                    // zero and inf are sticky under further multiplication by finite positive magnitudes: test per group of 4
-                    #pragma unroll 1
-                    for (int b = b0 + 8; b < M && prod != 0.0 && ! isinf (prod); b += 4)
-                    {
-                        #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                        {
-                            const double re = (double) (0.5f * (sm.ex[zpos<R1> (b + u)].x + sm.ex[zpos<R1> (N - b - u)].x));
-                            const double mg = re * re;
-                            if (mg > eps) prod *= mg;
-                        }
-                    }
-                    ev_code = (unsigned) t;
-                    ev_prod = prod;
-                }
+                if (left) { ev_code = (unsigned) t; ev_prod = prod; }
             }
             double s4[4] = { var, sie, flat_sum_thread, evar };
             warp_sum_t<4> (s4, lane);
@@ -679,12 +684,21 @@ k_analyse (const AnalyseParams p)
                 for (int n1 = 0; n1 < R1; ++n1)
                 {
                     const int c = n1 * 256 + T * q;
-                    const float x = __fmul_rn (sm.ring[(rb + c) & (N - 1)], gain);
                     const int idx = (c < M) ? c + t : (N - c) - t;                                // P is even: P[N - n] = P[n]
-                    io.v[q * R1 + n1] = make_float2 (x, __fmul_rn (sm.pa[idx], pscale));
+#if FX_P_GATHER
+                    io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[(rb + c) & (N - 1)], sm.pa[idx]), make_float2 (gain, pscale));
+#else
+                    io.v[q * R1 + n1] = make_float2 (__fmul_rn (sm.ring[(rb + c) & (N - 1)], gain), __fmul_rn (sm.pa[idx], pscale));
+#endif
                 }
         }
-        __syncthreads();                                            // ring and exchange buffer are free: prefetch the next hop
+        // No barrier here: stage 1 of the transform stores to this thread's own slots of the exchange buffer, which nobody
+        // reads between the barrier above (the split is complete) and the barrier inside the transform.
+        fft_core<R1> (io, t);
+        // (the record of this frame is written after the frame's last barrier, one part per warp)
+        __syncthreads();
+        // every read of the ring for this frame is complete (filter pass, gather of FFT-beta): prefetch the next hop; it
+        // lands during the pitch / harmonic passes
         if (f + 1 < f_end)
         {
             const long jn = j_new + 1;
@@ -705,9 +719,6 @@ k_analyse (const AnalyseParams p)
                 if (t == 0) mbar_arrive (&sm.mbar);
             }
         }
-        fft_core<R1> (io, t);
-        // (the record of this frame is written after the frame's last barrier, one part per warp)
-        __syncthreads();
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
         // workf holds d[s] (kept for the margins), workg receives cnd[s]; each thread owns s = 16 t .. 16 t + 15
@@ -1045,6 +1056,20 @@ k_analyse (const AnalyseParams p)
                 {
                     const int ev_warp = __ffs ((int) __ballot_sync (0xffffffffu, evc == ev)) - 1;
                     product = sm.ev_prod[ev_warp];
+                    // The reference keeps multiplying (:92).  The spectrum of a non-silent frame is in prev_g by now (written
+                    // before the last transform's barriers); a silent frame reports no flatness at all (:121-123).  32 bins per
+                    // step: each lane fetches one (a gated-out bin multiplies by exactly 1), then the warp replays them in order.
+                    if (! silent)
+                    {
+                        #pragma unroll 1
+                        for (int b = 8 * ((int) ev + 1); b < M && product != 0.0 && ! isinf (product); b += 32)
+                        {
+                            double mgl = 1.0;
+                            if (b + lane < M) { const double re = (double) prev_g[b + lane]; const double mg = re * re; if (mg > eps) mgl = mg; }
+                            #pragma unroll 1
+                            for (int i = 0; i < 32 && product != 0.0 && ! isinf (product); ++i) product *= __shfl_sync (0xffffffffu, mgl, i);
+                        }
+                    }
                     flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f);
                 }
                 if (lane == 0) { rec->product = product; rec->flat_state = silent ? 3.0f : flat_state; }
