@@ -130,6 +130,23 @@ __device__ __forceinline__ double div_by (double a, double b, double rb)
     const double q = a * rb;
     return fma (fma (-q, b, a), rb, q);
 }
+// floor (NN / d) for a power of two NN <= 4096 and 1 <= d <= NN through the fp32 reciprocal: exact quotients come out exact
+// (then d is a power of two and so is its reciprocal), every other quotient is at least 1 / d away from an integer while the
+// fp32 error is below NN / d * 2^-23.
+template <int NN> __device__ __forceinline__ int idiv_n (int d)
+{
+    return __float2int_rz ((float) NN * __frcp_rn ((float) d));
+}
+// a / b for moderate positive operands without the division subroutine: fp32 reciprocal seed, then quotient + exact residual
+// corrections (relative error 2^-22 -> 2^-44 -> 2^-66 before the final rounding).  Exact whenever a / b is representable.
+__device__ __forceinline__ double div_seeded (double a, double b)
+{
+    const double r0 = (double) __frcp_rn ((float) b);
+    double q = a * r0;
+    q = fma (fma (-q, b, a), r0, q);
+    q = fma (fma (-q, b, a), r0, q);
+    return fma (fma (-q, b, a), r0, q);
+}
 __device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
 {
     return (m * 2.0) * __hiloint2double ((e - 1 + 1023) << 20, 0);
@@ -231,6 +248,7 @@ template <int R1> struct Smem
     float    pmins[2][NW];           // pitch margin / runner-up partials
     unsigned short ndm[T];           // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178)
     double   ev_prod[NW];           // flatness product replayed by the warp's earliest range event
+    double   ev_chunk[32];          // 32 gated magnitudes of the product's continuation (record stage)
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     uint64_t mbar;
     const float2* tw1f;
@@ -263,6 +281,7 @@ k_analyse (const AnalyseParams p)
     using D = FftDims<R1>;
     using S = Smem<R1>;
     constexpr int N = D::N, M = N / 2, T = D::T, NW = T / 32, Q1 = D::Q1;
+    constexpr int LOG_N = R1 == 16 ? 12 : (R1 == 8 ? 11 : 10);
 
     S& sm = *reinterpret_cast<S*> (fx_smem_raw);
     float* workf = reinterpret_cast<float*> (sm.ex);          // fp32 view, skewed index phys (n)
@@ -697,6 +716,15 @@ k_analyse (const AnalyseParams p)
         fft_core<R1> (io, t);
         // (the record of this frame is written after the frame's last barrier, one part per warp)
         __syncthreads();
+        // The flatness product's continuation (record stage, below) starts from the spectrum bins behind the earliest event
+        // thread: its warp fetches the first 32 of them now, from the spectrum stored before the transform.
+        float ev_pf = 0.0f;
+        if (warp == 4 % NW)
+        {
+            const unsigned ev = warp_minu (lane < NW ? sm.ucodes[0][lane] : 0xffffffffu);
+            const int b = 8 * ((int) ev + 1) + lane;
+            if (ev != 0xffffffffu && ! silent && b < M) ev_pf = prev_g[b];
+        }
         // every read of the ring for this frame is complete (filter pass, gather of FFT-beta): prefetch the next hop; it
         // lands during the pitch / harmonic passes
         if (f + 1 < f_end)
@@ -849,8 +877,10 @@ k_analyse (const AnalyseParams p)
             const float c_right = (right < N) ? workg[phys (right)] : 0.0f;          // cnd[N] = Im part of lag 0 = 0
             lag_i = (c_end <= c_right) ? s_end : right;
             // margins (diagnostics), spread over the whole CTA: the threshold tests s = 2 .. s0 (:176) ...
+            // (work is dealt from the last warp backwards: the low lags meet the warp that has no peaks to process below)
+            const int tr = (t + 32) & (T - 1);
             #pragma unroll 1
-            for (int s = 2 + t; s <= (int) s0; s += T)
+            for (int s = 2 + tr; s <= (int) s0; s += T)
             {
                 const float c = workg[phys (s)];
                 pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[phys (s)], e_abs), 0.01f, 0.0f));
@@ -858,7 +888,7 @@ k_analyse (const AnalyseParams p)
             // ... and every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1
             const int s_hi = min (s_end + 1, N - 1);
             #pragma unroll 1
-            for (int s = (int) s0 + 1 + t; s <= s_hi; s += T)
+            for (int s = (int) s0 + 1 + tr; s <= s_hi; s += T)
             {
                 const float c = workg[phys (s)], cp = workg[phys (s - 1)];
                 const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
@@ -886,13 +916,15 @@ k_analyse (const AnalyseParams p)
             const float wpm = warp_min_nonneg (pm);
             if (lane == 0) sm.pmins[0][warp] = wpm;
         }
-        // f0 = sample rate / lag and the bins derived from it come from tables built on the host with the reference's own
-        // double arithmetic (PitchAnalyser.h:57, HarmonicCharacteristics.h:158-185,246-249): slot 0 stands for lag -1
+        // The harmonic and sub-octave bins of f0 = sample rate / lag come from a table built on the host with the reference's
+        // own double arithmetic (PitchAnalyser.h:57, HarmonicCharacteristics.h:158-185): slot 0 stands for lag -1
         const int lag_slot = lag_i < 0 ? 0 : lag_i;
-        const double2 f0_pair = __ldg (reinterpret_cast<const double2*> (p.f0_tab) + lag_slot);      // { f0, 1 / f0 }
-        const double f0 = f0_pair.x, inv_f0 = f0_pair.y;
         const short* htab = p.her_tab + (size_t) lag_slot * FX_HER_TAB_STRIDE;
-        const int f0_bin = (int) __ldg (&htab[18]);
+        // bin of f0 (:246-249): floor (f0 / frpb) is floor (N / lag) unless the quotient is an exact integer (lag a power of
+        // two), where the reference's fp64 rounding decides -- those few values come with the parameters.  No global load
+        // sits between the lag and the peak loop.
+        int f0_bin = -1;
+        if (lag_i > 0) f0_bin = (lag_i & (lag_i - 1)) ? idiv_n<N> (lag_i) : (int) p.f0bin_pow2[__ffs (lag_i) - 1];
         int her_bin = -1;
         if (warp == 0 && lane < 18) her_bin = (int) __ldg (&htab[lane]);       // consumed after the next barrier
 
@@ -900,24 +932,19 @@ k_analyse (const AnalyseParams p)
         const bool hsilent = hsum < 0.005;                                                        // :88
         const double mean_mag = hsum * inv_m;                                                     // :86
         {
-            double sum_normed = 0.0, inharm = 0.0;
+            double inharm = 0.0;                // sum of f0Proportion * binMagnitude; the record stage divides by the magnitude sum (:237)
             unsigned pgap = 0xffffffffu, peak_mask = 0u;
-            const double inv_hmax = 1.0 / hmax, inv_hsum = 1.0 / hsum;
             const float mean_f = (float) mean_mag;
             // neighbours bin-2, bin-1, bin+1 (:136-143, loop end exclusive)
             double mgs[11];
             #pragma unroll
             for (int j = 0; j < 11; ++j) mgs[j] = (double) ar[j] * (double) ar[j];
-            float nm[8];
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
                 const int bin = b0 + j;
                 const double mg = mgs[2 + j];
                 const float mgf = (float) mg;
-                const double e = mg * inv_hmax;                                                   // :75
-                nm[j] = (float) e;
-                sum_normed += e;
                 pgap = min (pgap, ulp_gap (mgf, mean_f));
                 if (mg > mean_mag)
                 {
@@ -933,7 +960,7 @@ k_analyse (const AnalyseParams p)
             }
             const int npeaks = __popc (peak_mask);
             // calculateInharmonicity (:212-244) over this thread's peaks
-            if (f0 > 0.0)                                                                         // :98
+            if (lag_i > 0)                                                                        // :98 f0 > 0
             {
                 #pragma unroll 1
                 while (peak_mask)
@@ -944,29 +971,58 @@ k_analyse (const AnalyseParams p)
                     if (bin == f0_bin) continue;                                                  // :220
                     const double re = (double) sm.pa[bin];                                        // still Re A: this thread's own bins
                     const double mg = re * re;
-                    double start_f = (double) bin * frpb;                                         // :223
-                    if (start_f == 0.0) start_f = frpb * 0.5;
-                    const double end_f = (double) (bin + 1) * frpb;
-                    // :251-259 higher / lower.  Above f0 (almost every peak) the divisor is f0, whose reciprocal comes from the
-                    // per-lag table: quotient, exact residual, one correction -- the correctly rounded quotient in 3 FMAs
-                    const double ra = (start_f == f0) ? 1.0 : (start_f > f0 ? div_by (start_f, f0, inv_f0) : f0 / start_f);
-                    const double rb = (end_f == f0) ? 1.0 : (end_f > f0 ? div_by (end_f, f0, inv_f0) : f0 / end_f);
-                    if (floor (ra) == floor (rb))                                                 // :232
+                    // :223-239 compares floor (higher / lower) for the two edges of the bin, start = bin frpb and end = (bin + 1) frpb,
+                    // against f0 = sample rate / lag.  Up to an ulp of fp64 rounding these ratios are the rationals bin lag / N
+                    // (bin above f0's) or N / (bin lag) (below): unless one of them is an exact integer -- where the reference's own
+                    // rounding decides -- their floors are the integer quotients and the fraction is a remainder, no fp64 division.
+                    const int pl = bin * lag_i, pl2 = pl + lag_i;
+                    bool exact_path = (bin == 0);                                                 // :224 start = frpb / 2
+                    int fa = 0, fb = 1;
+                    double frac = 0.0;
+                    if (bin > f0_bin)
                     {
-                        const double ratio = ra < rb ? ra : rb;
-                        inharm += (ratio - floor (ratio)) * (mg * inv_hsum);                      // :235-239
+                        exact_path = ((pl & (N - 1)) == 0) || ((pl2 & (N - 1)) == 0);
+                        fa = pl >> LOG_N; fb = pl2 >> LOG_N;
+                        frac = (double) (pl & (N - 1)) * (1.0 / (double) N);                      // the smaller ratio is the start edge's
                     }
+                    else if (bin > 0)
+                    {
+                        fa = idiv_n<N> (pl); fb = idiv_n<N> (pl2);
+                        const int rem2 = N - fb * pl2;
+                        exact_path = (N - fa * pl == 0) || (rem2 == 0);
+                        // the smaller ratio is the end edge's: fraction rem2 / pl2 (reciprocal seed from fp32, two residual corrections)
+                        const double dv2 = (double) pl2, r0 = (double) __frcp_rn ((float) pl2);
+                        double q = (double) rem2 * r0;
+                        q = fma (fma (-q, dv2, (double) rem2), r0, q);
+                        frac = fma (fma (-q, dv2, (double) rem2), r0, q);
+                    }
+                    if (exact_path)
+                    {
+                        const double2 f0_pair = __ldg (reinterpret_cast<const double2*> (p.f0_tab) + lag_slot);      // { f0, 1 / f0 }
+                        const double f0 = f0_pair.x, inv_f0 = f0_pair.y;
+                        double start_f = (double) bin * frpb;                                     // :223
+                        if (start_f == 0.0) start_f = frpb * 0.5;
+                        const double end_f = (double) (bin + 1) * frpb;
+                        // :251-259 higher / lower in the reference's own fp64 arithmetic
+                        const double ra = (start_f == f0) ? 1.0 : (start_f > f0 ? div_by (start_f, f0, inv_f0) : div_seeded (f0, start_f));
+                        const double rb = (end_f == f0) ? 1.0 : (end_f > f0 ? div_by (end_f, f0, inv_f0) : div_seeded (f0, end_f));
+                        if (floor (ra) == floor (rb))                                             // :232
+                        {
+                            const double ratio = ra < rb ? ra : rb;
+                            inharm += (ratio - floor (ratio)) * mg;                               // :235-239
+                        }
+                    }
+                    else if (fa == fb) inharm += frac * mg;
                 }
             }
             const float pkm = ulps_to_margin (pgap);
-            // normalised magnitudes replace Re A in place (nobody reads another thread's Re A after the barrier above)
-            *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (nm[0], nm[1], nm[2], nm[3]);
-            *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (nm[4], nm[5], nm[6], nm[7]);
-            double s2[2] = { sum_normed, inharm };
-            warp_sum_t<2> (s2, lane);
+            // (the normalised magnitudes of :71-77 are not materialised: their sum is magnitudeSum / maxMagnitude up to fp64
+            // rounding, and the few the harmonic energy terms look at are formed from Re A by the record stage)
+            double s1[1] = { inharm };
+            warp_sum<1> (s1);
             const int wnp = warp_addi (npeaks);
             const float wpk = warp_min_nonneg (pkm);
-            if (lane < 2) sm.red[1][6 + warp_sum_slot<2> (lane)][warp] = s2[0];                   // slots 6, 7: sum_normed, inharm
+            if (lane == 0) sm.red[1][7][warp] = s1[0];                                            // slot 7: inharmonicity sum
             if (lane == 0) { sm.ipeaks[warp] = wnp; sm.fmins[2][warp] = wpk; }
         }
         __syncthreads();
@@ -994,9 +1050,11 @@ k_analyse (const AnalyseParams p)
                 {
                     const int st = her_bin - 2 >= 0 ? her_bin - 2 : 0;
                     const int en = her_bin + 2 < M ? her_bin + 2 : M;
-                    float mx = sm.pa[her_bin];                                                    // :200-210
-                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, sm.pa[bb]);
-                    term = (double) mx;
+                    // :200-210 maximum of the normalised magnitudes (float) (mag / max) around the bin: the rounding to float is
+                    // monotone, so it is the normalised value of the largest |Re A|
+                    float mx = fabsf (sm.pa[her_bin]);
+                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, fabsf (sm.pa[bb]));
+                    term = (double) (float) (((double) mx * (double) mx) / hmax);                 // :75-76
                 }
                 // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
                 const double even = __shfl_sync (0xffffffffu, term, 16);
@@ -1007,7 +1065,7 @@ k_analyse (const AnalyseParams p)
             }
             if (warp == 1 % NW)
             {
-                const double sum_normed = sum_nw (ld ? sm.red[1][6][lane] : 0.0), inharm = sum_nw (ld ? sm.red[1][7][lane] : 0.0);
+                const double inharm = sum_nw (ld ? sm.red[1][7][lane] : 0.0);
                 const int npeaks = warp_addi (ld ? sm.ipeaks[lane] : 0);
                 const float pkm = warp_min_nonneg (ld ? sm.fmins[2][lane] : 1.0f);
                 float pmm = warp_min_nonneg (ld ? sm.pmins[0][lane] : 1.0f);
@@ -1016,7 +1074,7 @@ k_analyse (const AnalyseParams p)
                 if (lane == 0)
                 {
                     rec->lag = (float) lag_i; rec->pitch_margin = pmm;
-                    rec->hsum = hsum; rec->sum_normed = sum_normed; rec->inharm = inharm;
+                    rec->hsum = hsum; rec->sum_normed = hsum / hmax; rec->inharm = inharm / hsum;   // :77, :237
                     rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
                 }
             }
@@ -1056,18 +1114,32 @@ k_analyse (const AnalyseParams p)
                 {
                     const int ev_warp = __ffs ((int) __ballot_sync (0xffffffffu, evc == ev)) - 1;
                     product = sm.ev_prod[ev_warp];
-                    // The reference keeps multiplying (:92).  The spectrum of a non-silent frame is in prev_g by now (written
-                    // before the last transform's barriers); a silent frame reports no flatness at all (:121-123).  32 bins per
-                    // step: each lane fetches one (a gated-out bin multiplies by exactly 1), then the warp replays them in order.
+                    // The reference keeps multiplying (:92).  The spectrum of a non-silent frame is in prev_g (written before the
+                    // last transform's barriers); a silent frame reports no flatness at all (:121-123).  32 bins per step: each
+                    // lane holds one (a gated-out bin multiplies by exactly 1; the first 32 were fetched right after the
+                    // transform), then every lane replays them in order -- the same sequential IEEE products as the reference's.
                     if (! silent)
                     {
+                        int b = 8 * ((int) ev + 1);
+                        float re_f = ev_pf;
                         #pragma unroll 1
-                        for (int b = 8 * ((int) ev + 1); b < M && product != 0.0 && ! isinf (product); b += 32)
+                        for (;;)
                         {
                             double mgl = 1.0;
-                            if (b + lane < M) { const double re = (double) prev_g[b + lane]; const double mg = re * re; if (mg > eps) mgl = mg; }
+                            if (b + lane < M) { const double mg = (double) re_f * (double) re_f; if (mg > eps) mgl = mg; }
+                            // zero and inf are sticky under multiplication by finite positive magnitudes: test per group of 8
+                            sm.ev_chunk[lane] = mgl;
+                            __syncwarp();
                             #pragma unroll 1
-                            for (int i = 0; i < 32 && product != 0.0 && ! isinf (product); ++i) product *= __shfl_sync (0xffffffffu, mgl, i);
+                            for (int g = 0; g < 32 && product != 0.0 && ! isinf (product); g += 8)
+                            {
+                                #pragma unroll
+                                for (int i = 0; i < 8; ++i) product *= sm.ev_chunk[g + i];
+                            }
+                            __syncwarp();
+                            b += 32;
+                            if (b >= M || product == 0.0 || isinf (product)) break;
+                            re_f = (b + lane < M) ? prev_g[b + lane] : 0.0f;
                         }
                     }
                     flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f);

@@ -39,6 +39,7 @@ struct fx_engine
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw1f = nullptr;
     double *d_f0_tab = nullptr;
     short  *d_her_tab = nullptr;
+    short   f0bin_pow2[16] = {};
     double bin_var = 0.0;
     float  iir_c1 = 0.0f, iir_c2 = 0.0f;
 
@@ -275,6 +276,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
     a.tw1 = e->d_tw1; a.tw2 = e->d_tw2; a.tw1f = e->d_tw1f;
     a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab;
+    for (int k = 0; k < 16; ++k) a.f0bin_pow2[k] = e->f0bin_pow2[k];
     a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
     const size_t coff = (size_t) t0 * (size_t) n_chunks;
@@ -418,6 +420,7 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
     {
         std::vector<double> f0_tab; std::vector<short> her_tab;
         build_lag_tables (N, cfg->sample_rate, f0_tab, her_tab);
+        for (int k = 0; k < 16 && (1 << k) <= N; ++k) e->f0bin_pow2[k] = her_tab[(size_t) (1 << k) * FX_HER_TAB_STRIDE + 18];
         FX_CREATE (cudaMalloc (&e->d_f0_tab, f0_tab.size() * sizeof (double)));
         FX_CREATE (cudaMalloc (&e->d_her_tab, her_tab.size() * sizeof (short)));
         FX_CREATE (cudaMemcpy (e->d_f0_tab, f0_tab.data(), f0_tab.size() * sizeof (double), cudaMemcpyHostToDevice));

@@ -48,6 +48,7 @@ struct AnalyseParams
     // reference does not use it (HarmonicCharacteristics.h:158-185); [18] = bin of f0 itself (:246-249), clamped to a short
     const double* f0_tab;
     const short*  her_tab;
+    short        f0bin_pow2[16];   // her_tab[lag][18] for lag = 2^k (the lags whose f0 bin the kernel does not derive by integer division)
     // outputs
     FrameRec*    rec;              // [n_tracks][n_frames]
     float*       first_spec;       // [n_tracks][n_chunks][M]  Re spectrum (windowed path) of the chunk's first non-silent frame

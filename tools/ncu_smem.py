@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 4096 * 468
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "feature-extractor_b200/lib/libfxb200.so")], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("FXLIB", os.path.join(ROOT, "feature-extractor_b200/lib/libfxb200.so"))], cwd=tmp, capture_output=True)
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, "fx_analyse.sm_100a.cubin")], capture_output=True, text=True).stdout
 cur, infunc, a2l = None, False, {}
 for l in dis.split("\n"):
