@@ -969,6 +969,9 @@ k_analyse (const AnalyseParams p)
                     peak_mask &= peak_mask - 1u;
                     const int bin = b0 + j;
                     if (bin == f0_bin) continue;                                                  // :220
+                    // bin 0 (:224 start = frpb / 2): the start edge's ratio is exactly twice the end edge's, and that one is N / lag >= 1,
+                    // so their floors always differ (:232) and the bin contributes nothing
+                    if (bin == 0) continue;
                     const double re = (double) sm.pa[bin];                                        // still Re A: this thread's own bins
                     const double mg = re * re;
                     // :223-239 compares floor (higher / lower) for the two edges of the bin, start = bin frpb and end = (bin + 1) frpb,
@@ -976,7 +979,7 @@ k_analyse (const AnalyseParams p)
                     // (bin above f0's) or N / (bin lag) (below): unless one of them is an exact integer -- where the reference's own
                     // rounding decides -- their floors are the integer quotients and the fraction is a remainder, no fp64 division.
                     const int pl = bin * lag_i, pl2 = pl + lag_i;
-                    bool exact_path = (bin == 0);                                                 // :224 start = frpb / 2
+                    bool exact_path = false;
                     int fa = 0, fb = 1;
                     double frac = 0.0;
                     if (bin > f0_bin)
@@ -985,16 +988,15 @@ k_analyse (const AnalyseParams p)
                         fa = pl >> LOG_N; fb = pl2 >> LOG_N;
                         frac = (double) (pl & (N - 1)) * (1.0 / (double) N);                      // the smaller ratio is the start edge's
                     }
-                    else if (bin > 0)
+                    else
                     {
                         fa = idiv_n<N> (pl); fb = idiv_n<N> (pl2);
                         const int rem2 = N - fb * pl2;
                         exact_path = (N - fa * pl == 0) || (rem2 == 0);
-                        // the smaller ratio is the end edge's: fraction rem2 / pl2 (reciprocal seed from fp32, two residual corrections)
-                        const double dv2 = (double) pl2, r0 = (double) __frcp_rn ((float) pl2);
-                        double q = (double) rem2 * r0;
-                        q = fma (fma (-q, dv2, (double) rem2), r0, q);
-                        frac = fma (fma (-q, dv2, (double) rem2), r0, q);
+                        // the smaller ratio is the end edge's: fraction rem2 / pl2 < 1 from the fp32 reciprocal with one residual
+                        // correction (relative error ~1e-7 on a term whose sum is compared at 1e-4)
+                        const float r0 = __frcp_rn ((float) pl2), q0 = (float) rem2 * r0;
+                        frac = (double) fmaf (fmaf (-q0, (float) pl2, (float) rem2), r0, q0);
                     }
                     if (exact_path)
                     {
