@@ -123,29 +123,12 @@ __device__ __forceinline__ float rcp_approx (float x)
     asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// a / b given rb = RN (1 / b): q0 = a rb, exact residual a - q0 b, one correction.  Exact whenever a / b is representable
-// (integer frequency ratios: the floor tests of the inharmonicity measure), correctly rounded otherwise up to rare ties.
-__device__ __forceinline__ double div_by (double a, double b, double rb)
-{
-    const double q = a * rb;
-    return fma (fma (-q, b, a), rb, q);
-}
 // floor (NN / d) for a power of two NN <= 4096 and 1 <= d <= NN through the fp32 reciprocal: exact quotients come out exact
 // (then d is a power of two and so is its reciprocal), every other quotient is at least 1 / d away from an integer while the
 // fp32 error is below NN / d * 2^-23.
 template <int NN> __device__ __forceinline__ int idiv_n (int d)
 {
     return __float2int_rz ((float) NN * __frcp_rn ((float) d));
-}
-// a / b for moderate positive operands without the division subroutine: fp32 reciprocal seed, then quotient + exact residual
-// corrections (relative error 2^-22 -> 2^-44 -> 2^-66 before the final rounding).  Exact whenever a / b is representable.
-__device__ __forceinline__ double div_seeded (double a, double b)
-{
-    const double r0 = (double) __frcp_rn ((float) b);
-    double q = a * r0;
-    q = fma (fma (-q, b, a), r0, q);
-    q = fma (fma (-q, b, a), r0, q);
-    return fma (fma (-q, b, a), r0, q);
 }
 __device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
 {
@@ -1000,19 +983,13 @@ k_analyse (const AnalyseParams p)
                     }
                     if (exact_path)
                     {
-                        const double2 f0_pair = __ldg (reinterpret_cast<const double2*> (p.f0_tab) + lag_slot);      // { f0, 1 / f0 }
-                        const double f0 = f0_pair.x, inv_f0 = f0_pair.y;
-                        double start_f = (double) bin * frpb;                                     // :223
-                        if (start_f == 0.0) start_f = frpb * 0.5;
-                        const double end_f = (double) (bin + 1) * frpb;
-                        // :251-259 higher / lower in the reference's own fp64 arithmetic
-                        const double ra = (start_f == f0) ? 1.0 : (start_f > f0 ? div_by (start_f, f0, inv_f0) : div_seeded (f0, start_f));
-                        const double rb = (end_f == f0) ? 1.0 : (end_f > f0 ? div_by (end_f, f0, inv_f0) : div_seeded (f0, end_f));
-                        if (floor (ra) == floor (rb))                                             // :232
-                        {
-                            const double ratio = ra < rb ? ra : rb;
-                            inharm += (ratio - floor (ratio)) * mg;                               // :235-239
-                        }
+                        // an edge ratio may be an exact integer: the reference's fp64 rounding decides, and its value for this
+                        // (lag, bin) comes from the table the host evaluated in the reference's arithmetic
+                        const int sh = LOG_N - (__ffs (lag_i) - 1);                               // log2 (N / gcd (lag, N))
+                        int idx;
+                        if (bin > f0_bin) idx = (bin & ((1 << sh) - 1)) == 0 ? 2 * (bin >> sh) : 2 * ((bin + 1) >> sh) + 1;
+                        else              idx = (bin & (bin - 1)) == 0 ? 2 * (__ffs (bin) - 1) - 26 : 2 * (__ffs (bin + 1) - 1) + 1 - 26;
+                        inharm += __ldg (p.ex_tab + (__ldg (p.ex_off + lag_i) + idx)) * mg;
                     }
                     else if (fa == fb) inharm += frac * mg;
                 }

@@ -38,6 +38,8 @@ struct fx_engine
 
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw1f = nullptr;
     double *d_f0_tab = nullptr;
+    double *d_ex_tab = nullptr;
+    int    *d_ex_off = nullptr;
     short  *d_her_tab = nullptr;
     short   f0bin_pow2[16] = {};
     double bin_var = 0.0;
@@ -179,6 +181,57 @@ void build_lag_tables (int N, double sample_rate, std::vector<double>& f0_tab, s
     }
 }
 
+// Inharmonicity fractions for the (lag, bin) pairs whose edge ratios may be exact integers -- there the reference's own fp64
+// rounding decides on which side of the integer a ratio lands, so the value is taken from the reference's arithmetic, evaluated
+// here (HarmonicCharacteristics.h:223-236, :251-259), instead of being derived on the GPU.  Layout per lag (step = N / gcd (lag, N)):
+//   [ex_off[lag] + 2 q]     bin = q step      (start edge: bin lag is a multiple of N)
+//   [ex_off[lag] + 2 q + 1] bin = q step - 1  (end edge: (bin + 1) lag is a multiple of N),   q = 0 .. M / step
+// and, for lag = 2^b only, 2 * 13 entries in front of them for the bins below f0's:
+//   [ex_off[lag] - 26 + 2 a] bin = 2^a,  [ex_off[lag] - 26 + 2 a + 1] bin = 2^a - 1   (bin lag or (bin + 1) lag divides N)
+void build_exact_ratio_table (int N, double sample_rate, std::vector<double>& ex_tab, std::vector<int>& ex_off)
+{
+    const int M = N / 2;
+    const double nyquist = sample_rate / 2.0;
+    const double frpb = nyquist / (double) M;
+    auto ratio = [] (double f1, double f2)                         // getFrequencyRatio (:251-259)
+    {
+        if (f1 == f2) return 1.0;
+        const double higher = f1 > f2 ? f1 : f2;
+        const double lower = higher == f1 ? f2 : f1;
+        return higher / lower;
+    };
+    auto fraction = [&] (int bin, double f0)                       // :223-236
+    {
+        if (bin < 0 || bin >= M) return 0.0;
+        double start = (double) bin * frpb;
+        if (start == 0.0) start = frpb * 0.5;
+        const double end = (double) (bin + 1) * frpb;
+        const double ra = ratio (start, f0), rb = ratio (end, f0);
+        if (floor (ra) != floor (rb)) return 0.0;
+        const double r = ra < rb ? ra : rb;
+        return r - floor (r);
+    };
+    ex_tab.clear();
+    ex_off.assign ((size_t) N + 1, 0);
+    for (int lag = 1; lag <= N; ++lag)
+    {
+        const double f0 = (nyquist * 2.0) / (double) lag;           // PitchAnalyser.h:57
+        const int g = lag & -lag, step = N / g;
+        if ((lag & (lag - 1)) == 0)
+            for (int a = 0; a < 13; ++a)
+            {
+                ex_tab.push_back (fraction (1 << a, f0));
+                ex_tab.push_back (fraction ((1 << a) - 1, f0));
+            }
+        ex_off[(size_t) lag] = (int) ex_tab.size();
+        for (int q = 0; q <= M / step; ++q)
+        {
+            ex_tab.push_back (fraction (q * step, f0));
+            ex_tab.push_back (fraction (q * step - 1, f0));
+        }
+    }
+}
+
 fx_status upload_params (fx_engine* e, cudaStream_t s)
 {
     if (! e->params_dirty) return FX_OK;
@@ -275,7 +328,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
     a.tw1 = e->d_tw1; a.tw2 = e->d_tw2; a.tw1f = e->d_tw1f;
-    a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab;
+    a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab; a.ex_tab = e->d_ex_tab; a.ex_off = e->d_ex_off;
     for (int k = 0; k < 16; ++k) a.f0bin_pow2[k] = e->f0bin_pow2[k];
     a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
@@ -324,7 +377,7 @@ void free_engine (fx_engine* e)
     if (! e) return;
     cudaSetDevice (e->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_tw1f); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab);
+    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_tw1f); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab); cudaFree (e->d_ex_tab); cudaFree (e->d_ex_off);
     cudaFree (e->d_gain); cudaFree (e->d_mult); cudaFree (e->d_type); cudaFree (e->d_hist); cudaFree (e->d_reset);
     for (int i = 0; i < 2; ++i) { cudaFree (e->d_tail[i]); cudaFree (e->d_prev[i]); cudaFree (e->d_hrows[i]); }
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
@@ -421,6 +474,12 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
         std::vector<double> f0_tab; std::vector<short> her_tab;
         build_lag_tables (N, cfg->sample_rate, f0_tab, her_tab);
         for (int k = 0; k < 16 && (1 << k) <= N; ++k) e->f0bin_pow2[k] = her_tab[(size_t) (1 << k) * FX_HER_TAB_STRIDE + 18];
+        std::vector<double> ex_tab; std::vector<int> ex_off;
+        build_exact_ratio_table (N, cfg->sample_rate, ex_tab, ex_off);
+        FX_CREATE (cudaMalloc (&e->d_ex_tab, ex_tab.size() * sizeof (double)));
+        FX_CREATE (cudaMalloc (&e->d_ex_off, ex_off.size() * sizeof (int)));
+        FX_CREATE (cudaMemcpy (e->d_ex_tab, ex_tab.data(), ex_tab.size() * sizeof (double), cudaMemcpyHostToDevice));
+        FX_CREATE (cudaMemcpy (e->d_ex_off, ex_off.data(), ex_off.size() * sizeof (int), cudaMemcpyHostToDevice));
         FX_CREATE (cudaMalloc (&e->d_f0_tab, f0_tab.size() * sizeof (double)));
         FX_CREATE (cudaMalloc (&e->d_her_tab, her_tab.size() * sizeof (short)));
         FX_CREATE (cudaMemcpy (e->d_f0_tab, f0_tab.data(), f0_tab.size() * sizeof (double), cudaMemcpyHostToDevice));

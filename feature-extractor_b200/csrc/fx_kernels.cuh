@@ -48,6 +48,8 @@ struct AnalyseParams
     // reference does not use it (HarmonicCharacteristics.h:158-185); [18] = bin of f0 itself (:246-249), clamped to a short
     const double* f0_tab;
     const short*  her_tab;
+    const double* ex_tab;          // inharmonicity fractions of the (lag, bin) pairs with exact-integer edge ratios (fx_engine.cu: build_exact_ratio_table)
+    const int*    ex_off;          // [window + 1] offset of a lag's entries in ex_tab
     short        f0bin_pow2[16];   // her_tab[lag][18] for lag = 2^k (the lags whose f0 bin the kernel does not derive by integer division)
     // outputs
     FrameRec*    rec;              // [n_tracks][n_frames]

@@ -206,6 +206,39 @@ def test_edge_cases(fx, oracle):
     assert ou.close(g["raw"][1], o["raw"][1]).all()                     # DC: every feature agrees
 
 
+@pytest.mark.parametrize("N,H,sr", [(4096, 1024, 48000.0), (2048, 1024, 48000.0), (1024, 512, 44100.0)])
+def test_inharmonicity_at_exact_integer_ratios(fx, oracle, N, H, sr):
+    """Pitch lags that share a large factor with the window (sr / 2^k and neighbours like 3 * 2^k): many peak bins then have an
+    edge whose ratio to f0 is an exact integer, where the reference's own fp64 rounding decides whether a multiple of f0 lies in
+    the bin (HarmonicCharacteristics.h:223-236).  The GPU takes those (lag, bin) values from a table evaluated on the host in
+    the reference's arithmetic; everything else is integer arithmetic.  Rich harmonic signals put peaks on those bins."""
+    # a sine of period 4 L is analysed with lag L (the first threshold crossing is a quarter period); its own bin N / (4 L)
+    # lies below f0's with bin * lag = N / 4, and the weak partials at 8, 12, 16, 20 cycles per 4 L sit on multiples of f0
+    lags = [l for l in (16, 32, 64, 128, 256, 48, 96, 192, 80, 160, 320, 112, 224) if 4 * l < N]
+    S = 16 * H
+    n = np.arange(S, dtype=np.float64)
+    rng = np.random.default_rng(7)
+    rows = []
+    for l in lags:
+        period = 4.0 * l
+        x = 0.5 * np.sin(2 * np.pi * n / period + 0.3)
+        for k, a in ((8, 0.02), (12, 0.02), (16, 0.015), (20, 0.01)):
+            if k / period < 0.45:
+                x += a * np.sin(2 * np.pi * k * n / period + rng.uniform(0, 2 * np.pi))
+        rows.append(x + 0.0005 * rng.uniform(-1, 1, S))
+    audio = np.stack(rows).astype(np.float32)
+    o = oracle.analyse(audio, window=N, hop=H, sample_rate=sr)
+    with fx.Engine(n_tracks=len(lags), window=N, hop=H, sample_rate=sr) as e:
+        g = e.analyse_host(audio)
+    res = ou.compare(g, o)
+    assert_parity(res, f"exact-ratio lags N={N}", max_exempt_frac=0.25)
+    # the case must actually be exercised: several tracks are analysed at lags that share a factor >= 16 with the window
+    glag = g["diag"][..., ou.D["lag"]].astype(np.int64)
+    special = ((glag > 0) & ((glag & -glag) >= 16)).any(axis=1)
+    assert special.sum() >= 4, glag[:, -1]
+    assert (g["raw"][..., ou.F["inharm"]] > 0).any()
+
+
 def test_runtime_parameters(fx, oracle):
     """gain, onset type / window / sensitivity, single RMS push: same surface as the reference's setters."""
     N, H, sr, T = 2048, 1024, 48000.0, 6
