@@ -123,12 +123,14 @@ __device__ __forceinline__ float rcp_approx (float x)
     asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// floor (NN / d) for a power of two NN <= 4096 and 1 <= d <= NN through the fp32 reciprocal: exact quotients come out exact
-// (then d is a power of two and so is its reciprocal), every other quotient is at least 1 / d away from an integer while the
-// fp32 error is below NN / d * 2^-23.
-template <int NN> __device__ __forceinline__ int idiv_n (int d)
+// floor (NN / d) for 1 <= d <= NN <= 4096 from an approximate fp32 reciprocal r of d (relative error a few 2^-23: the estimate is
+// off by at most one, and one comparison settles it).
+template <int NN> __device__ __forceinline__ int idiv_n (int d, float r)
 {
-    return __float2int_rz ((float) NN * __frcp_rn ((float) d));
+    int q = __float2int_rz ((float) NN * r);
+    q += ((q + 1) * d <= NN) ? 1 : 0;
+    q -= (q * d > NN) ? 1 : 0;
+    return q;
 }
 __device__ __forceinline__ double ldexp_normal (double m, int e)       // m in [0.5, 1), result a normal double
 {
@@ -907,7 +909,8 @@ k_analyse (const AnalyseParams p)
         // two), where the reference's fp64 rounding decides -- those few values come with the parameters.  No global load
         // sits between the lag and the peak loop.
         int f0_bin = -1;
-        if (lag_i > 0) f0_bin = (lag_i & (lag_i - 1)) ? idiv_n<N> (lag_i) : (int) p.f0bin_pow2[__ffs (lag_i) - 1];
+        if (lag_i > 0) f0_bin = (lag_i & (lag_i - 1)) ? idiv_n<N> (lag_i, rcp_approx ((float) lag_i)) : (int) p.f0bin_pow2[__ffs (lag_i) - 1];
+        const int ex_base = __ldg (p.ex_off + lag_slot);          // this lag's entries of the exact-ratio table (used below, rarely)
         int her_bin = -1;
         if (warp == 0 && lane < 18) her_bin = (int) __ldg (&htab[lane]);       // consumed after the next barrier
 
@@ -973,13 +976,15 @@ k_analyse (const AnalyseParams p)
                     }
                     else
                     {
-                        fa = idiv_n<N> (pl); fb = idiv_n<N> (pl2);
+                        // (not a rare case: a frame analysed at a short lag has every peak below f0's bin)
+                        const float plf2 = (float) pl2, r1 = rcp_approx ((float) pl), r2 = rcp_approx (plf2);
+                        fa = idiv_n<N> (pl, r1); fb = idiv_n<N> (pl2, r2);
                         const int rem2 = N - fb * pl2;
                         exact_path = (N - fa * pl == 0) || (rem2 == 0);
                         // the smaller ratio is the end edge's: fraction rem2 / pl2 < 1 from the fp32 reciprocal with one residual
                         // correction (relative error ~1e-7 on a term whose sum is compared at 1e-4)
-                        const float r0 = __frcp_rn ((float) pl2), q0 = (float) rem2 * r0;
-                        frac = (double) fmaf (fmaf (-q0, (float) pl2, (float) rem2), r0, q0);
+                        const float q0 = (float) rem2 * r2;
+                        frac = (double) fmaf (fmaf (-q0, plf2, (float) rem2), r2, q0);
                     }
                     if (exact_path)
                     {
@@ -989,7 +994,7 @@ k_analyse (const AnalyseParams p)
                         int idx;
                         if (bin > f0_bin) idx = (bin & ((1 << sh) - 1)) == 0 ? 2 * (bin >> sh) : 2 * ((bin + 1) >> sh) + 1;
                         else              idx = (bin & (bin - 1)) == 0 ? 2 * (__ffs (bin) - 1) - 26 : 2 * (__ffs (bin + 1) - 1) + 1 - 26;
-                        inharm += __ldg (p.ex_tab + (__ldg (p.ex_off + lag_i) + idx)) * mg;
+                        inharm += __ldg (p.ex_tab + (ex_base + idx)) * mg;
                     }
                     else if (fa == fb) inharm += frac * mg;
                 }
