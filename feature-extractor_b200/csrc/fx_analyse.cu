@@ -1036,8 +1036,10 @@ k_analyse (const AnalyseParams p)
                     const int en = her_bin + 2 < M ? her_bin + 2 : M;
                     // :200-210 maximum of the normalised magnitudes (float) (mag / max) around the bin: the rounding to float is
                     // monotone, so it is the normalised value of the largest |Re A|
-                    float mx = fabsf (sm.pa[her_bin]);
-                    for (int bb = st; bb < en; ++bb) mx = fmaxf (mx, fabsf (sm.pa[bb]));
+                    // (the window [st, en) holds at most bins c - 2 .. c + 1: four independent loads, indices clamped into the window)
+                    const float m0 = fabsf (sm.pa[her_bin]), m1 = fabsf (sm.pa[max (her_bin - 2, st)]), m2 = fabsf (sm.pa[max (her_bin - 1, st)]);
+                    const float m3 = fabsf (sm.pa[min (her_bin + 1, en - 1)]);
+                    const float mx = fmaxf (fmaxf (m0, m1), fmaxf (m2, m3));
                     term = (double) (float) (((double) mx * (double) mx) / hmax);                 // :75-76
                 }
                 // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
@@ -1058,7 +1060,7 @@ k_analyse (const AnalyseParams p)
                 if (lane == 0)
                 {
                     rec->lag = (float) lag_i; rec->pitch_margin = pmm;
-                    rec->hsum = hsum; rec->sum_normed = hsum / hmax; rec->inharm = inharm / hsum;   // :77, :237
+                    rec->hsum = hsum; rec->hmax = hmax; rec->inharm = inharm;                     // K1b divides (:77, :237)
                     rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
                 }
             }
@@ -1189,14 +1191,15 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
     float o_her = 0.0f, o_oer = 0.0f, o_inh = 0.0f;
     if (! (r.hsum < 0.005))
     {
-        double her = r.score / r.sum_normed;                                                      // :186-188
+        // the normalised magnitudes (:71-77) sum to magnitudeSum / maxMagnitude up to fp64 rounding
+        double her = r.score / (r.hsum / r.hmax);                                                 // :186-188
         her = her > 1.0 ? 1.0 : her; her = her < 0.0 ? 0.0 : her;
         double oer = 1.0;
         if (r.odd > 0.0) oer = r.even / r.odd;                                                    // :190-195
         oer = oer > 1.0 ? 1.0 : oer; oer = oer < 0.0 ? 0.0 : oer;
         o_her = (float) log10 ((double) (float) her * 9.0 + 1.0);                                 // :101-103
         o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);
-        o_inh = (float) log10 (r.inharm * 9.0 + 1.0);
+        o_inh = (float) log10 ((r.inharm / r.hsum) * 9.0 + 1.0);                                  // :237 (K1 leaves the sum of f0Proportion * binMagnitude)
     }
     gate_margin = fminf (gate_margin, relmargin_d (r.hsum, 0.005));
 

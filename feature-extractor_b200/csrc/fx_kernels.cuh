@@ -15,7 +15,7 @@ constexpr int kMaxOnsetHist = 16;
 struct FrameRec
 {
     double rms_sum, mag_sum, weighted, flux, lhr, flat_sum, count, product, var, sie, mean_e, evar, max_e;   // spectral body
-    double hsum, sum_normed, inharm, score, even, odd;                                                       // harmonic body
+    double hsum, hmax, inharm, score, even, odd;                                                             // harmonic body
     float  centroid, flat_margin, flat_state, have_prev, lag, pitch_margin, npeaks, peak_margin;
 };
 
