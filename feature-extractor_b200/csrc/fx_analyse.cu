@@ -1029,25 +1029,20 @@ k_analyse (const AnalyseParams p)
                 // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
                 // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3 (bins from the table, -1 = not used: a sub-octave in
                 // f0's own bin is skipped (:163-164), harmonics stop at the first bin >= M (:174-175)); the sums are warp reductions
-                double term = 0.0;
+                float mx = -1.0f;                                                                 // "term not used"
                 if (her_bin >= 0 && ! hsilent)
                 {
                     const int st = her_bin - 2 >= 0 ? her_bin - 2 : 0;
                     const int en = her_bin + 2 < M ? her_bin + 2 : M;
                     // :200-210 maximum of the normalised magnitudes (float) (mag / max) around the bin: the rounding to float is
-                    // monotone, so it is the normalised value of the largest |Re A|
+                    // monotone, so it is the normalised value of the largest |Re A|, which is what the record keeps; K1b
+                    // normalises and sums the 18 terms in the reference's order.
                     // (the window [st, en) holds at most bins c - 2 .. c + 1: four independent loads, indices clamped into the window)
                     const float m0 = fabsf (sm.pa[her_bin]), m1 = fabsf (sm.pa[max (her_bin - 2, st)]), m2 = fabsf (sm.pa[max (her_bin - 1, st)]);
                     const float m3 = fabsf (sm.pa[min (her_bin + 1, en - 1)]);
-                    const float mx = fmaxf (fmaxf (m0, m1), fmaxf (m2, m3));
-                    term = (double) (float) (((double) mx * (double) mx) / hmax);                 // :75-76
+                    mx = fmaxf (fmaxf (m0, m1), fmaxf (m2, m3));
                 }
-                // score = all 18 terms; even = harmonic 2; odd = harmonics 1 and 3 (:190-195)
-                const double even = __shfl_sync (0xffffffffu, term, 16);
-                const double odd = __shfl_sync (0xffffffffu, term, 15) + __shfl_sync (0xffffffffu, term, 17);
-                double s1[1] = { term };
-                warp_sum<1> (s1);
-                if (lane == 0) { rec->score = s1[0]; rec->even = even; rec->odd = odd; }
+                if (lane < 18) rec->her_mx[lane] = mx;
             }
             if (warp == 1 % NW)
             {
@@ -1191,11 +1186,23 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
     float o_her = 0.0f, o_oer = 0.0f, o_inh = 0.0f;
     if (! (r.hsum < 0.005))
     {
+        // calculateHarmonicEnergyCharacteristics (:147-198): 15 sub-octave terms, then the harmonics 1..3; each term is the
+        // normalised magnitude (float) (mag / max) (:75-76) of the largest |Re A| K1 found around its bin (< 0: term not used)
+        double score = 0.0, even = 0.0, odd = 0.0;
+        #pragma unroll
+        for (int l = 0; l < 18; ++l)
+        {
+            const float mx = r.her_mx[l];
+            const double term = mx < 0.0f ? 0.0 : (double) (float) (((double) mx * (double) mx) / r.hmax);
+            score += term;
+            if (l == 16) even = term;                                                             // harmonic 2
+            if (l == 15 || l == 17) odd += term;                                                  // harmonics 1 and 3
+        }
         // the normalised magnitudes (:71-77) sum to magnitudeSum / maxMagnitude up to fp64 rounding
-        double her = r.score / (r.hsum / r.hmax);                                                 // :186-188
+        double her = score / (r.hsum / r.hmax);                                                   // :186-188
         her = her > 1.0 ? 1.0 : her; her = her < 0.0 ? 0.0 : her;
         double oer = 1.0;
-        if (r.odd > 0.0) oer = r.even / r.odd;                                                    // :190-195
+        if (odd > 0.0) oer = even / odd;                                                          // :190-195
         oer = oer > 1.0 ? 1.0 : oer; oer = oer < 0.0 ? 0.0 : oer;
         o_her = (float) log10 ((double) (float) her * 9.0 + 1.0);                                 // :101-103
         o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);

@@ -15,8 +15,9 @@ constexpr int kMaxOnsetHist = 16;
 struct FrameRec
 {
     double rms_sum, mag_sum, weighted, flux, lhr, flat_sum, count, product, var, sie, mean_e, evar, max_e;   // spectral body
-    double hsum, hmax, inharm, score, even, odd;                                                             // harmonic body
+    double hsum, hmax, inharm;                                                                               // harmonic body
     float  centroid, flat_margin, flat_state, have_prev, lag, pitch_margin, npeaks, peak_margin;
+    float  her_mx[18];             // largest |Re A| around the 15 sub-octave and 3 harmonic bins of f0 (HarmonicCharacteristics.h:147-210), < 0: not used
 };
 
 // ---- K1: per-(track, chunk) frame walker ------------------------------------------------------------
