@@ -225,7 +225,8 @@ template <int R1> struct Smem
     double   scan_m[NW];             // flatness product scan, warp totals
     int      scan_e[NW];
     double   pscan[NW];              // pitch cumulative sum scan, warp totals
-    unsigned long long keys[NW];
+    unsigned ubest[NW];             // smallest cnd of the lag search range, warp minima (bit patterns)
+    unsigned ugidx[NW];             // first index holding it (only formed when no lag crosses the threshold)
     unsigned ucodes[2][NW];
     float    fmins[3][NW];           // [0] flatness gate margin, [1] max |Re|, |Im| of the lower bins (slope quirk), [2] peak margin
     float    fmaxs[NW];
@@ -777,7 +778,7 @@ k_analyse (const AnalyseParams p)
             for (int w = 0; w < NW; ++w) if (w < warp) base += sm.pscan[w];
             // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
             float sumf = (float) base;
-            float best = 100.0f; int best_j = -1;
+            float best = 100.0f;
             unsigned cross = 0u;
             float c_before = 0.0f;
             #pragma unroll
@@ -793,18 +794,15 @@ k_analyse (const AnalyseParams p)
                 if (j >= 2 || t != 0)                                                             // the search starts at s = 2 (:169)
                 {
                     if (c < 0.01f) cross |= 1u << j;                                              // :176
-                    if (c < best) { best = c; best_j = j; }                                       // :171-175 first strict minimum
+                    best = fminf (best, c);                                                       // :171-175 (its index only matters when no lag crosses: found then)
                 }
             }
             sm.ndm[t] = (unsigned short) nd_mask;
             if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
-            const unsigned best_s = best_j < 0 ? 0xffffffffu : (unsigned) (16 * t + best_j);
-            // first strict minimum of the warp: smallest value (cnd >= 0 orders like its bit pattern), then smallest index
+            // smallest cnd of the warp (cnd >= 0 orders like its bit pattern)
             const unsigned wfc = warp_minu (first_cross);
             const unsigned wbest = warp_minu (__float_as_uint (best));
-            const unsigned widx = warp_minu (__float_as_uint (best) == wbest ? best_s : 0xffffffffu);
-            const unsigned long long wkey = ((unsigned long long) wbest << 32) | widx;
-            if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.keys[warp] = wkey; }
+            if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.ubest[warp] = wbest; }
         }
         // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69).  The three
         // neighbours the peak test needs from other threads (bins b0 - 2, b0 - 1, b0 + 8) are fetched now: after the next
@@ -828,13 +826,13 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
         unsigned s0 = 0xffffffffu;
-        unsigned long long gkey = ~0ull;
+        unsigned gbest = 0xffffffffu;                              // bit pattern of the smallest cnd of the search range
         double hsum = 0.0; float hmaxre = 0.0f;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
             s0 = min (s0, sm.ucodes[1][w]);
-            gkey = sm.keys[w] < gkey ? sm.keys[w] : gkey;
+            gbest = min (gbest, sm.ubest[w]);
             hsum += sm.red[0][5][w]; hmaxre = fmaxf (hmaxre, sm.fmaxs[w]);
         }
         const double hmax = (double) hmaxre * (double) hmaxre;
@@ -883,7 +881,18 @@ k_analyse (const AnalyseParams p)
         }
         else
         {
-            const unsigned gidx = (unsigned) (gkey & 0xffffffffull);
+            // No lag crossed the threshold (:188-189, rare): the lag is the first strict global minimum (:171-175), the smallest
+            // index among the lags that hold the smallest value.  One more block reduction, in this CTA-uniform branch only.
+            unsigned mine = 0xffffffffu;
+            #pragma unroll
+            for (int j = 15; j >= 0; --j)
+                if ((j >= 2 || t != 0) && __float_as_uint (workg[17 * t + j]) == gbest) mine = (unsigned) (16 * t + j);
+            const unsigned wmine = warp_minu (mine);
+            if (lane == 0) sm.ugidx[warp] = wmine;
+            __syncthreads();
+            unsigned gidx = 0xffffffffu;
+            #pragma unroll
+            for (int w = 0; w < NW; ++w) gidx = min (gidx, sm.ugidx[w]);
             lag_i = (gidx == 0xffffffffu) ? -1 : (int) gidx;
             // no crossing: every threshold test was false; runner-up of the global minimum for its margin
             float second = 100.0f;
@@ -1051,7 +1060,7 @@ k_analyse (const AnalyseParams p)
                 const float pkm = warp_min_nonneg (ld ? sm.fmins[2][lane] : 1.0f);
                 float pmm = warp_min_nonneg (ld ? sm.pmins[0][lane] : 1.0f);
                 const float second = warp_min_nonneg (ld ? sm.pmins[1][lane] : 100.0f);
-                if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float ((unsigned) (gkey >> 32)), second));
+                if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float (gbest), second));
                 if (lane == 0)
                 {
                     rec->lag = (float) lag_i; rec->pitch_margin = pmm;
