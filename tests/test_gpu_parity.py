@@ -239,6 +239,27 @@ def test_inharmonicity_at_exact_integer_ratios(fx, oracle, N, H, sr):
     assert (g["raw"][..., ou.F["inharm"]] > 0).any()
 
 
+def test_nan_sample_takes_the_no_crossing_branch(fx, oracle):
+    """A NaN sample makes every cnd value of its frames NaN: no lag crosses the threshold and no value is a strict minimum, so the
+    reference reports lag -1 (PitchAnalyser.h:165,188) and f0 = -sr; the frames before and after are untouched.  This is the only
+    way into the kernel's no-crossing branch on finite-length frames (a running sum cannot keep growing 1 % per lag)."""
+    N, H, sr = 2048, 1024, 48000.0
+    x = ou.make_tracks(3, 12 * H, sr)
+    x[1, 5 * H + 10] = np.nan
+    o = oracle.analyse(x, window=N, hop=H, sample_rate=sr)
+    with fx.Engine(n_tracks=3, window=N, hop=H, sample_rate=sr) as e:
+        g = e.analyse_host(x)
+    assert_parity(ou.compare(g, o), "NaN sample")
+    assert (g["diag"][1, 5:7, ou.D["lag"]] == -1).all() and (o["diag"][1, 5:7, ou.D["lag"]] == -1).all()
+    assert np.array_equal(np.isnan(g["raw"]), np.isnan(o["raw"]))
+    assert np.array_equal(g["raw"][[0, 2]], fx_clean(fx, x[[0, 2]], N, H, sr))          # the other tracks do not notice
+
+
+def fx_clean(fx, x, N, H, sr):
+    with fx.Engine(n_tracks=x.shape[0], window=N, hop=H, sample_rate=sr) as e:
+        return e.analyse_host(np.ascontiguousarray(x))["raw"]
+
+
 def test_runtime_parameters(fx, oracle):
     """gain, onset type / window / sensitivity, single RMS push: same surface as the reference's setters."""
     N, H, sr, T = 2048, 1024, 48000.0, 6
