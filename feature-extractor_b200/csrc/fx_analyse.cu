@@ -1215,7 +1215,9 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         oer = oer > 1.0 ? 1.0 : oer; oer = oer < 0.0 ? 0.0 : oer;
         o_her = (float) log10 ((double) (float) her * 9.0 + 1.0);                                 // :101-103
         o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);
-        o_inh = (float) log10 ((r.inharm / r.hsum) * 9.0 + 1.0);                                  // :237 (K1 leaves the sum of f0Proportion * binMagnitude)
+        // :237 (K1 leaves the sum of f0Proportion * binMagnitude; with no contributing peak the reference's sum stays 0 whatever
+        // the magnitude sum is -- NaN input included)
+        o_inh = (float) log10 ((r.inharm != 0.0 ? r.inharm / r.hsum : 0.0) * 9.0 + 1.0);
     }
     gate_margin = fminf (gate_margin, relmargin_d (r.hsum, 0.005));
 
