@@ -26,16 +26,6 @@
 #include "fx_kernels.cuh"
 #include <math.h>
 
-#ifndef FX_P_FILTER
-#define FX_P_FILTER 1
-#endif
-#ifndef FX_P_GATHER
-#define FX_P_GATHER 1
-#endif
-#ifndef FX_P_SPLIT
-#define FX_P_SPLIT 0
-#endif
-
 namespace fx {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -421,11 +411,7 @@ k_analyse (const AnalyseParams p)
                 // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
                 // (packed multiply: both sequences by the same ramp value.  What is stored is z / 2 -- see the split below)
                 const float w = fmaf ((float) j, wseg_d, wseg_0);
-#if FX_P_FILTER
                 sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = f2mul (make_float2 (__fmul_rn (xs[j], gain), ys[j]), make_float2 (w, w));   // tpos (16 t + j)
-#else
-                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = make_float2 (__fmul_rn (__fmul_rn (xs[j], gain), w), __fmul_rn (ys[j], w));
-#endif
             }
         }
         __syncthreads();
@@ -465,12 +451,7 @@ k_analyse (const AnalyseParams p)
             {
                 const float2 zk = sm.ex[zb_own + zrun<R1> (j)];                                // Z[k], k = b0 + j
                 const float2 zn = sm.ex[j == 0 ? zb_self : zb_mirror + zrun<R1> (8 - j)];      // Z[(N - k) & (N - 1)]
-#if FX_P_SPLIT
-                const float2 bc = f2add (zk, zn);                                               // (Re B, Re C): the 1/2 is in the window
-                const float reB = bc.x, reC = bc.y;
-#else
                 const float reB = zk.x + zn.x, reC = zk.y + zn.y;
-#endif
                 const float imB = zk.y - zn.y;
                 cr[j] = reB;
                 if (b0 < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
@@ -690,11 +671,7 @@ k_analyse (const AnalyseParams p)
                 {
                     const int c = n1 * 256 + T * q;
                     const int idx = (c < M) ? c + t : (N - c) - t;                                // P is even: P[N - n] = P[n]
-#if FX_P_GATHER
                     io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[(rb + c) & (N - 1)], sm.pa[idx]), make_float2 (gain, pscale));
-#else
-                    io.v[q * R1 + n1] = make_float2 (__fmul_rn (sm.ring[(rb + c) & (N - 1)], gain), __fmul_rn (sm.pa[idx], pscale));
-#endif
                 }
         }
         // No barrier here: stage 1 of the transform stores to this thread's own slots of the exchange buffer, which nobody
