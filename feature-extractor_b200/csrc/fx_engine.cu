@@ -286,25 +286,30 @@ fx_status ensure_records (fx_engine* e, long frames)
     return FX_OK;
 }
 
-// how many chunks per track: enough CTAs for a few waves over the machine, but never chunks so short that the
-// window refill at a chunk start dominates
+// How many chunks per track.  All CTAs carry equal work, so the launch takes ceil (CTAs / resident slots) rounds and an almost
+// empty last round costs a whole chunk's time: 4096 tracks on 444 slots are 9.2 rounds as whole tracks but 36.9 as quarters.
+// Against that, every chunk start refills the whole window and repeats the prologue (about two frames' worth).  Among the
+// chunk counts that give at least a few rounds over the machine take the one with the best fill x (1 - start-up share); never
+// chunks shorter than 8 frames.
 int choose_chunks (const fx_engine* e, long n_tracks, long frames)
 {
-    const long target = (long) e->sm_count * e->ctas_per_sm * 6;
-    if (n_tracks >= target || frames <= 8) return 1;
-    long c = (target + n_tracks - 1) / n_tracks;
+    if (frames <= 8 || n_tracks <= 0) return 1;
+    if (const char* f = getenv ("FXB200_CHUNKS")) { const long k = atol (f); if (k >= 1 && k <= (frames + 7) / 8) return (int) k; }   // tuning aid
+    const long slots = (long) e->sm_count * e->ctas_per_sm;
+    const long target = slots * 6;
     const long max_c = (frames + 7) / 8;
+    long c = (target + n_tracks - 1) / n_tracks;
     if (c > max_c) c = max_c;
     if (c < 1) c = 1;
-    // among the next few chunk counts take the one whose last wave of CTAs is fullest (all CTAs carry equal work, so an
-    // almost empty last wave costs a whole chunk's time)
-    const long slots = (long) e->sm_count * e->ctas_per_sm;
-    long best_c = c; double best_fill = 0.0;
-    for (long k = c; k <= c + 4 && k <= max_c; ++k)
+    const double startup_frames = 2.0;
+    long best_c = c; double best_score = 0.0;
+    for (long k = c; k <= c + 8 && k <= max_c; ++k)
     {
-        const long ctas = n_tracks * k, waves = (ctas + slots - 1) / slots;
-        const double fill = (double) ctas / (double) (waves * slots);
-        if (fill > best_fill + 1e-9) { best_fill = fill; best_c = k; }
+        const long ctas = n_tracks * k, rounds = (ctas + slots - 1) / slots;
+        const double fill = (double) ctas / (double) (rounds * slots);
+        const double fpc = (double) ((frames + k - 1) / k);
+        const double score = fill * fpc / (fpc + startup_frames);
+        if (score > best_score + 1e-9) { best_score = score; best_c = k; }
     }
     return (int) best_c;
 }
