@@ -37,7 +37,6 @@ struct fx_engine
     std::atomic<uint64_t> launches{0};
 
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw1f = nullptr;
-    double *d_f0_tab = nullptr;
     double *d_ex_tab = nullptr;
     int    *d_ex_off = nullptr;
     short  *d_her_tab = nullptr;
@@ -146,20 +145,17 @@ void build_twiddles (int N, std::vector<float2>& tw1, std::vector<float2>& tw2, 
 }
 
 // f0 and the harmonic bins as functions of the integer lag, in the reference's arithmetic (see AnalyseParams)
-void build_lag_tables (int N, double sample_rate, std::vector<double>& f0_tab, std::vector<short>& her_tab)
+void build_lag_tables (int N, double sample_rate, std::vector<short>& her_tab)
 {
     const int M = N / 2;
     const double nyquist = sample_rate / 2.0;
     const double frpb = nyquist / (double) M;                       // HarmonicCharacteristics.h:53
-    f0_tab.assign (2 * ((size_t) N + 1), 0.0);                    // { f0, 1 / f0 } per slot
     her_tab.assign ((size_t) (N + 1) * FX_HER_TAB_STRIDE, (short) -1);
     auto clamp_short = [] (double v) { return (short) (v > 32767.0 ? 32767.0 : (v < -32768.0 ? -32768.0 : v)); };
     for (int slot = 0; slot <= N; ++slot)
     {
         const double lag = slot == 0 ? -1.0 : (double) slot;
         const double f0 = (nyquist * 2.0) / lag;                    // PitchAnalyser.h:57
-        f0_tab[2 * (size_t) slot] = f0;
-        f0_tab[2 * (size_t) slot + 1] = 1.0 / f0;
         short* row = her_tab.data() + (size_t) slot * FX_HER_TAB_STRIDE;
         const double f0_bin_d = floor (f0 / frpb);                  // :246-249
         row[18] = clamp_short (f0_bin_d);
@@ -333,7 +329,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, const float* d_
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;
     a.tw1 = e->d_tw1; a.tw2 = e->d_tw2; a.tw1f = e->d_tw1f;
-    a.f0_tab = e->d_f0_tab; a.her_tab = e->d_her_tab; a.ex_tab = e->d_ex_tab; a.ex_off = e->d_ex_off;
+    a.her_tab = e->d_her_tab; a.ex_tab = e->d_ex_tab; a.ex_off = e->d_ex_off;
     for (int k = 0; k < 16; ++k) a.f0bin_pow2[k] = e->f0bin_pow2[k];
     a.rec = e->d_rec + (size_t) t0 * (size_t) frames;
     // chunk buffers are indexed by (local track, chunk); each range uses its own slice keyed by t0
@@ -382,7 +378,7 @@ void free_engine (fx_engine* e)
     if (! e) return;
     cudaSetDevice (e->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_tw1f); cudaFree (e->d_f0_tab); cudaFree (e->d_her_tab); cudaFree (e->d_ex_tab); cudaFree (e->d_ex_off);
+    cudaFree (e->d_tw1); cudaFree (e->d_tw2); cudaFree (e->d_tw1f); cudaFree (e->d_her_tab); cudaFree (e->d_ex_tab); cudaFree (e->d_ex_off);
     cudaFree (e->d_gain); cudaFree (e->d_mult); cudaFree (e->d_type); cudaFree (e->d_hist); cudaFree (e->d_reset);
     for (int i = 0; i < 2; ++i) { cudaFree (e->d_tail[i]); cudaFree (e->d_prev[i]); cudaFree (e->d_hrows[i]); }
     cudaFree (e->d_first_spec); cudaFree (e->d_last_spec); cudaFree (e->d_first_idx);
@@ -476,8 +472,8 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
     FX_CREATE (cudaMalloc (&e->d_tw1f, tw1f.size() * sizeof (float2)));
     FX_CREATE (cudaMemcpy (e->d_tw1f, tw1f.data(), tw1f.size() * sizeof (float2), cudaMemcpyHostToDevice));
     {
-        std::vector<double> f0_tab; std::vector<short> her_tab;
-        build_lag_tables (N, cfg->sample_rate, f0_tab, her_tab);
+        std::vector<short> her_tab;
+        build_lag_tables (N, cfg->sample_rate, her_tab);
         for (int k = 0; k < 16 && (1 << k) <= N; ++k) e->f0bin_pow2[k] = her_tab[(size_t) (1 << k) * FX_HER_TAB_STRIDE + 18];
         std::vector<double> ex_tab; std::vector<int> ex_off;
         build_exact_ratio_table (N, cfg->sample_rate, ex_tab, ex_off);
@@ -485,9 +481,7 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
         FX_CREATE (cudaMalloc (&e->d_ex_off, ex_off.size() * sizeof (int)));
         FX_CREATE (cudaMemcpy (e->d_ex_tab, ex_tab.data(), ex_tab.size() * sizeof (double), cudaMemcpyHostToDevice));
         FX_CREATE (cudaMemcpy (e->d_ex_off, ex_off.data(), ex_off.size() * sizeof (int), cudaMemcpyHostToDevice));
-        FX_CREATE (cudaMalloc (&e->d_f0_tab, f0_tab.size() * sizeof (double)));
         FX_CREATE (cudaMalloc (&e->d_her_tab, her_tab.size() * sizeof (short)));
-        FX_CREATE (cudaMemcpy (e->d_f0_tab, f0_tab.data(), f0_tab.size() * sizeof (double), cudaMemcpyHostToDevice));
         FX_CREATE (cudaMemcpy (e->d_her_tab, her_tab.data(), her_tab.size() * sizeof (short), cudaMemcpyHostToDevice));
     }
 

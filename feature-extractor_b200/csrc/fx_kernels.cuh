@@ -44,10 +44,9 @@ struct AnalyseParams
     const float2* tw2;
     const float2* tw1f;            // stage-1 twiddles in full, [(k1 - 1) * 256 + m] = W_N^(m k1) (the two-factor product, rounded as the kernel used to), read through L1
     // per-lag tables, slot lag = 1 .. window, slot 0 = "no lag found" (lag -1), evaluated on the host in the reference's own
-    // double arithmetic:  f0_tab[2 lag] = (nyquist * 2) / lag  (PitchAnalyser.h:57), f0_tab[2 lag + 1] = its reciprocal
+    // double arithmetic from f0 = (nyquist * 2) / lag (PitchAnalyser.h:57):
     // her_tab[lag][0..14] = bin of the sub-octave f0 / 2^(l+1), [15..17] = bin of the harmonic h f0, h = 1..3, or -1 when the
     // reference does not use it (HarmonicCharacteristics.h:158-185); [18] = bin of f0 itself (:246-249), clamped to a short
-    const double* f0_tab;
     const short*  her_tab;
     const double* ex_tab;          // inharmonicity fractions of the (lag, bin) pairs with exact-integer edge ratios (fx_engine.cu: build_exact_ratio_table)
     const int*    ex_off;          // [window + 1] offset of a lag's entries in ex_tab
