@@ -8,6 +8,7 @@ import numpy as np, fxb200, oracle_util as ou
 for N, H, sr in ((4096, 1024, 48000.0), (2048, 512, 48000.0), (1024, 512, 44100.0)):
     T = 10
     audio = ou.make_tracks(T, 12 * H, sr)
+    audio[3, 5 * H + 7] = np.nan          # the lag search's no-crossing branch (one more block barrier) runs for these frames
     with fxb200.Engine(n_tracks=T, window=N, hop=H, sample_rate=sr) as e:
         g = e.analyse_host(audio)
     print(N, H, g["frames"], float(np.nansum(g["raw"][..., 1])))
