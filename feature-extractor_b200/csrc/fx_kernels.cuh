@@ -103,6 +103,7 @@ struct SmoothParams
     const int*   onset_hist;
     const float* onset_mult;
     const long*  onset_reset;      // [n_tracks] absolute frame index at which the onset histories were last cleared
+    const long*  track_start;      // [n_tracks] absolute frame index at which the track's own stream started (may be null: 0)
     float*       latest;           // [n_tracks][12 + 2] smoothed vector of the newest frame + 64-bit frame count as two words (may be null)
 };
 cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t stream);
@@ -136,8 +137,11 @@ __host__ __device__ inline int pcm_bytes_per_sample (int format)
 }
 
 // ---- synthetic workload ------------------------------------------------------------------------------
-cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
+cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track, long first_sample,
                           double sample_rate, uint64_t seed, cudaStream_t stream);
+
+// ---- gain change between calls: rescale the carried overlap of the tracks whose ratio is not 1 ----------
+cudaError_t launch_tail_scale (float* tail, long tail_len, const float* ratio, long n_tracks, cudaStream_t stream);
 
 // ---- FP32 FMA microbenchmark ---------------------------------------------------------------------------
 cudaError_t measure_fp32_peak (double* tflops);

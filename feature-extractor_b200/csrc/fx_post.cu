@@ -4,6 +4,7 @@
 //   K3  k_smooth     AudioFeatures / ValueHistory moving averages (RealTimeAnalyser.h:70-88,
 //                    RealTimeAudioAnalysis.h:40-96) and OnsetDetector (SpectralCharacteristics.h:243-306)
 //       k_hist       carry the last raw rows to the next call
+//       k_tail_scale a gain change between calls: carried overlap rescaled to the gain it was collected at
 //       k_synth      synthetic workload generator -- measurement support only
 // All citations relative to /root/reference/Source/.
 #include "fx_kernels.cuh"
@@ -81,21 +82,22 @@ __device__ __forceinline__ const float* raw_row (const SmoothParams& p, long tra
 
 // smoothed RMS as RealTimeSpectralAnalyser::detectOnset reads it (RealTimeAnalyser.h:239): after the spectral
 // body's push of frame j, before the harmonic body's
-__device__ __forceinline__ float amp_at_spectral_time (const SmoothParams& p, long track, long j)
+__device__ __forceinline__ float amp_at_spectral_time (const SmoothParams& p, long track, long j, long start)
 {
     float total = 0.0f;
+    const long jr = j - start;                                  // frames of this track before frame j
     if (p.rms_pushes >= 2)
     {
-        if (j - 5 >= 0) total += raw_row (p, track, j - 5)[FX_RMS];
+        if (j - 5 >= start) total += raw_row (p, track, j - 5)[FX_RMS];
         for (long q = j - 4; q < j; ++q)
-            if (q >= 0) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
+            if (q >= start) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
         total += raw_row (p, track, j)[FX_RMS];
-        const long rec = 2 * j + 1 < 10 ? 2 * j + 1 : 10;
+        const long rec = 2 * jr + 1 < 10 ? 2 * jr + 1 : 10;
         return total / (float) (int) rec;
     }
     for (long q = j - 9; q <= j; ++q)
-        if (q >= 0) total += raw_row (p, track, q)[FX_RMS];
-    const long rec = j + 1 < 10 ? j + 1 : 10;
+        if (q >= start) total += raw_row (p, track, q)[FX_RMS];
+    const long rec = jr + 1 < 10 ? jr + 1 : 10;
     return total / (float) (int) rec;
 }
 
@@ -111,7 +113,10 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
     if (idx >= n_tracks * p.n_frames) return;
     const long track = idx / p.n_frames;
     const int f = (int) (idx % p.n_frames);
-    const long g = p.frames_before + f;                       // absolute frame index since stream start
+    const long g = p.frames_before + f;                       // absolute frame index of the track group's stream
+    // hop at which this track's own stream started (a controller created while the engine runs): earlier frames do not
+    // exist for it -- fresh ValueHistory objects have recorded nothing (RealTimeAudioAnalysis.h:40-96)
+    const long start = p.track_start ? p.track_start[track] : 0;
     float* row = p.raw + (track * p.n_frames + f) * FX_NUM_FEATURES;
 
     // ---- onset (spectral body, after the flux / RMS pushes of frame g) -----------------------------------
@@ -119,14 +124,15 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
     const int type = p.onset_type[track];
     const float mult = p.onset_mult[track];
     float onset = 0.0f, om = 1.0f;
-    if (g - p.onset_reset[track] + 1 >= L)                    // SpectralCharacteristics.h:253-258: histories full
+    const long onset_from = p.onset_reset[track] > start ? p.onset_reset[track] : start;
+    if (g - onset_from + 1 >= L)                              // SpectralCharacteristics.h:253-258: histories full
     {
         float am[kMaxOnsetHist], sf[kMaxOnsetHist];
         float tot_am = 0.0f, tot_sf = 0.0f;
         for (int i = 0; i < L; ++i)
         {
             const long j = g - L + 1 + i;
-            am[i] = amp_at_spectral_time (p, track, j);
+            am[i] = amp_at_spectral_time (p, track, j, start);
             sf[i] = 0.0f + raw_row (p, track, j)[FX_FLUX];    // depth-1 history: getValue = (0 + v) / 1
             tot_am += am[i];                                  // ValueHistory::getTotal, oldest first
             tot_sf += sf[i];
@@ -158,7 +164,8 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
 
     // ---- AudioFeatures::getValue for every slot, after both analyser bodies of frame g -------------------
     float sm[FX_NUM_FEATURES];
-    const long rec10 = g + 1 < 10 ? g + 1 : 10;
+    const long gr = g - start;                                // frames of this track before this one
+    const long rec10 = gr + 1 < 10 ? gr + 1 : 10;
     for (int k = 0; k < FX_NUM_FEATURES; ++k)
     {
         float total = 0.0f;
@@ -167,14 +174,14 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
         else if (k == FX_RMS && p.rms_pushes >= 2)
         {
             for (long q = g - 4; q <= g; ++q)
-                if (q >= 0) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
-            const long rec = 2 * (g + 1) < 10 ? 2 * (g + 1) : 10;
+                if (q >= start) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
+            const long rec = 2 * (gr + 1) < 10 ? 2 * (gr + 1) : 10;
             sm[k] = total / (float) (int) rec;
         }
         else
         {
             for (long q = g - 9; q <= g; ++q)
-                if (q >= 0) total += raw_row (p, track, q)[k];
+                if (q >= start) total += raw_row (p, track, q)[k];
             sm[k] = total / (float) (int) rec10;                                          // :84-88
         }
     }
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
     {
         float* lo = p.latest + track * (FX_NUM_FEATURES + 2);
         for (int k = 0; k < FX_NUM_FEATURES; ++k) lo[k] = sm[k];
-        const unsigned long long cnt = (unsigned long long) (g + 1);
+        const unsigned long long cnt = (unsigned long long) (gr + 1);      // hops of this track analysed so far
         lo[FX_NUM_FEATURES]     = __uint_as_float ((unsigned) (cnt & 0xffffffffull));
         lo[FX_NUM_FEATURES + 1] = __uint_as_float ((unsigned) (cnt >> 32));
     }
@@ -202,7 +209,8 @@ __global__ void __launch_bounds__ (128) k_hist (const SmoothParams p, long n_tra
     const long track = idx / (FX_NUM_FEATURES * kHistRows);
     const long j = p.frames_before + p.n_frames - kHistRows + i;
     float v = 0.0f;
-    if (j >= 0 && j >= p.frames_before - kHistRows) v = raw_row (p, track, j)[k];
+    const long start = p.track_start ? p.track_start[track] : 0;
+    if (j >= start && j >= p.frames_before - kHistRows) v = raw_row (p, track, j)[k];
     p.hist_out[(track * kHistRows + i) * FX_NUM_FEATURES + k] = v;
 }
 
@@ -217,6 +225,26 @@ cudaError_t launch_smooth (long n_tracks, const SmoothParams& p, cudaStream_t st
     }
     const long ht = n_tracks * kHistRows * FX_NUM_FEATURES;
     k_hist<<<(unsigned) ((ht + 127) / 128), 128, 0, stream>>> (p, n_tracks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A gain change between two calls: the overlap carried in `tail` was collected at the old gain (AudioDataCollector.h:88
+// multiplies on the way out of the ring, so the older part of the next windows keeps it) while K1 applies the track's
+// current gain to the whole window.  Scaling the carried samples by old / new once restores the reference's mixed-gain
+// windows up to two fp32 roundings per sample.
+__global__ void __launch_bounds__ (256) k_tail_scale (float* tail, long tail_len, const float* __restrict__ ratio)
+{
+    const float r = ratio[blockIdx.x];
+    if (r == 1.0f) return;
+    float* row = tail + (long) blockIdx.x * tail_len;
+    for (long i = threadIdx.x; i < tail_len; i += blockDim.x) row[i] *= r;
+}
+
+cudaError_t launch_tail_scale (float* tail, long tail_len, const float* ratio, long n_tracks, cudaStream_t stream)
+{
+    if (n_tracks <= 0 || tail_len <= 0) return cudaSuccess;
+    k_tail_scale<<<(unsigned) n_tracks, 256, 0, stream>>> (tail, tail_len, ratio);
     return cudaGetLastError();
 }
 
@@ -236,14 +264,44 @@ __device__ __forceinline__ void philox4x32_10 (uint32_t c0, uint32_t c1, uint32_
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void __launch_bounds__ (256) k_synth (float* audio, long track_stride, long n_samples, long n_tracks,
-                                                 long first_track, double sample_rate, uint64_t seed)
+// sin (2 pi r) for r in [0, 1) from IEEE double add / multiply only (explicit _rn intrinsics: no FMA contraction), so that
+// the test suite reproduces every sample bit for bit with numpy (tests: synth_tracks): quadrant q = floor (4 r + 1/2),
+// z = r - q / 4 in [-1/8, 1/8], Taylor polynomials of sin / cos in a = 2 pi z (|a| <= pi / 4: truncation < 1e-11).
+__device__ __forceinline__ double synth_sin_turns (double r)
 {
+    const double q = floor (__dadd_rn (__dmul_rn (4.0, r), 0.5));
+    const double z = __dadd_rn (r, -__dmul_rn (0.25, q));
+    const double a = __dmul_rn (z, 6.283185307179586);
+    const double a2 = __dmul_rn (a, a);
+    double ps = -2.505210838544172e-08;                                                   // -1/11!
+    ps = __dadd_rn (__dmul_rn (ps, a2),  2.755731922398589e-06);                          //  1/9!
+    ps = __dadd_rn (__dmul_rn (ps, a2), -1.984126984126984e-04);                          // -1/7!
+    ps = __dadd_rn (__dmul_rn (ps, a2),  8.333333333333333e-03);                          //  1/5!
+    ps = __dadd_rn (__dmul_rn (ps, a2), -1.666666666666667e-01);                          // -1/3!
+    ps = __dadd_rn (__dmul_rn (ps, a2),  1.0);
+    const double sn = __dmul_rn (a, ps);
+    double pc = -2.755731922398589e-07;                                                   // -1/10!
+    pc = __dadd_rn (__dmul_rn (pc, a2),  2.480158730158730e-05);                          //  1/8!
+    pc = __dadd_rn (__dmul_rn (pc, a2), -1.388888888888889e-03);                          // -1/6!
+    pc = __dadd_rn (__dmul_rn (pc, a2),  4.166666666666666e-02);                          //  1/4!
+    pc = __dadd_rn (__dmul_rn (pc, a2), -0.5);
+    pc = __dadd_rn (__dmul_rn (pc, a2),  1.0);
+    const int qi = ((int) q) & 3;
+    return qi == 0 ? sn : (qi == 1 ? pc : (qi == 2 ? -sn : -pc));
+}
+
+struct SynthFreqs { double f[48]; };     // 110 * 2^(k / 12), evaluated on the host (exp2 is not correctly rounded everywhere)
+
+__global__ void __launch_bounds__ (256) k_synth (float* audio, long track_stride, long n_samples, long n_tracks,
+                                                 long first_track, long first_sample, double sample_rate, uint64_t seed, const SynthFreqs fr)
+{
+    // first_sample is a multiple of 4: one Philox block yields the four samples 4 c .. 4 c + 3 of the stream
     const long quads = (n_samples + 3) / 4;
     const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_tracks * quads) return;
     const long tl = idx / quads;
-    const long n0 = (idx % quads) * 4;
+    const long i0 = (idx % quads) * 4;                                                    // index inside this call's buffer
+    const long n0 = first_sample + i0;                                                    // index inside the stream
     const long track = first_track + tl;
     const uint64_t key = seed ^ (uint64_t) track;
     uint32_t r[4];
@@ -251,30 +309,35 @@ __global__ void __launch_bounds__ (256) k_synth (float* audio, long track_stride
 
     const int reg = (int) (track & 7);
     const double sigma = reg == 6 ? 0.5 : (reg == 7 ? 0.001 : 0.05);                      // the three flatness regimes
-    const double freq = 110.0 * exp2 ((double) (track % 48) / 12.0);
-    double ph = (double) track * 0.61803398874989484820;
-    ph -= floor (ph);                                                                     // phi_t / (2 pi)
+    const double freq = fr.f[track % 48];
+    double ph = __dmul_rn ((double) track, 0.61803398874989484820);
+    ph = __dadd_rn (ph, -floor (ph));                                                     // phi_t / (2 pi)
     const long sr = (long) sample_rate;
     float* dst = audio + tl * track_stride;
     #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
         const long n = n0 + i;
-        if (n >= n_samples) break;
-        const double u = (double) (r[i] >> 8) * (1.0 / 8388608.0) - 1.0;                  // uniform [-1, 1)
-        double x = 0.5 * sinpi (2.0 * (freq * (double) n / sample_rate + ph)) + sigma * u;
-        if ((n % sr) < sr / 20) x *= 4.0;                                                 // burst at the top of every second (onsets)
+        if (i0 + i >= n_samples) break;
+        const double u = __dadd_rn (__dmul_rn ((double) (r[i] >> 8), 1.0 / 8388608.0), -1.0);   // uniform [-1, 1), exact
+        double turns = __dadd_rn (__ddiv_rn (__dmul_rn (freq, (double) n), sample_rate), ph);
+        turns = __dadd_rn (turns, -floor (turns));
+        double x = __dadd_rn (__dmul_rn (0.5, synth_sin_turns (turns)), __dmul_rn (sigma, u));
+        if ((n % sr) < sr / 20) x = __dmul_rn (x, 4.0);                                   // burst at the top of every second (onsets)
         if ((track & 1) && (n % (2 * sr)) >= sr && (n % (2 * sr)) < sr + sr / 4) x = 0.0; // 0.25 s of silence every 2 s on odd tracks
-        dst[n] = (float) x;
+        dst[i0 + i] = (float) x;
     }
 }
 
-cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track,
+cudaError_t launch_synth (float* d_audio, long track_stride, long n_samples, long n_tracks, long first_track, long first_sample,
                           double sample_rate, uint64_t seed, cudaStream_t stream)
 {
     const long total = n_tracks * ((n_samples + 3) / 4);
     if (total <= 0) return cudaSuccess;
-    k_synth<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>> (d_audio, track_stride, n_samples, n_tracks, first_track, sample_rate, seed);
+    if (first_sample & 3) return cudaErrorInvalidValue;
+    SynthFreqs fr;
+    for (int k = 0; k < 48; ++k) fr.f[k] = 110.0 * pow (2.0, (double) k / 12.0);
+    k_synth<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>> (d_audio, track_stride, n_samples, n_tracks, first_track, first_sample, sample_rate, seed, fr);
     return cudaGetLastError();
 }
 

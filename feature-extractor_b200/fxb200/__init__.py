@@ -32,6 +32,8 @@ EXPORTS = (
     "fx_poll_features", "fx_flush", "fx_osc_order", "fx_synth_device", "fx_kernel_launches",
     "fx_profile_enable", "fx_profile_read", "fx_measure_fp32_peak",
     "fx_pcm_bytes_per_sample", "fx_analyse_host_pcm", "fx_decode_pcm_device",
+    "fx_poll_block", "fx_rt_start", "fx_rt_stop", "fx_set_features_callback", "fx_set_track_active", "fx_clear_buffer",
+    "fx_set_sample_rate", "fx_rt_get_stats", "fx_osc_encode_tracks", "fx_synth_device_at", "fx_h2d_probe",
 )
 
 # fx_engine.h FX_PCM_*: sample encodings of WAV (little endian) and AIFF (big endian) data chunks
@@ -44,6 +46,13 @@ class Config(ctypes.Structure):
         ("rms_pushes_per_frame", c_int), ("onset_type", c_int), ("onset_hist", c_int), ("onset_multiplier", c_float),
         ("gain", c_float), ("max_frames_per_call", c_long), ("ring_hops", c_int), ("tracks_per_group", c_int),
     ]
+
+
+class RtStats(ctypes.Structure):
+    _fields_ = [("batches", c_uint64), ("hops", c_uint64), ("overruns", c_uint64), ("batch_ms_mean", c_double), ("batch_ms_max", c_double)]
+
+
+FEATURES_CALLBACK = ctypes.CFUNCTYPE(None, c_void_p, c_int, c_int, c_uint64, c_int)
 
 
 class FxError(RuntimeError):
@@ -109,6 +118,28 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.fx_analyse_host_pcm.restype = c_int
     lib.fx_decode_pcm_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_void_p, c_long, c_void_p]
     lib.fx_decode_pcm_device.restype = c_int
+    lib.fx_poll_block.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.fx_poll_block.restype = c_int
+    lib.fx_rt_start.argtypes = [c_void_p]
+    lib.fx_rt_start.restype = c_int
+    lib.fx_rt_stop.argtypes = [c_void_p]
+    lib.fx_rt_stop.restype = c_int
+    lib.fx_set_features_callback.argtypes = [c_void_p, FEATURES_CALLBACK, c_void_p]
+    lib.fx_set_features_callback.restype = c_int
+    lib.fx_set_track_active.argtypes = [c_void_p, c_int, c_int, c_int]
+    lib.fx_set_track_active.restype = c_int
+    lib.fx_clear_buffer.argtypes = [c_void_p, c_int]
+    lib.fx_clear_buffer.restype = c_int
+    lib.fx_set_sample_rate.argtypes = [c_void_p, c_double]
+    lib.fx_set_sample_rate.restype = c_int
+    lib.fx_rt_get_stats.argtypes = [c_void_p, POINTER(RtStats), c_int]
+    lib.fx_rt_get_stats.restype = c_int
+    lib.fx_osc_encode_tracks.argtypes = [c_void_p, POINTER(c_int), c_int, POINTER(c_char_p), c_int, c_void_p, c_int, POINTER(c_int)]
+    lib.fx_osc_encode_tracks.restype = c_int
+    lib.fx_synth_device_at.argtypes = [c_void_p, c_void_p, c_long, c_long, c_long, c_long, c_uint64, c_void_p]
+    lib.fx_synth_device_at.restype = c_int
+    lib.fx_h2d_probe.argtypes = [c_int, c_long, c_int, c_int, POINTER(c_double)]
+    lib.fx_h2d_probe.restype = c_int
     if path is None:
         _lib = lib
     return lib
@@ -167,6 +198,15 @@ class Engine:
 
     def reset(self):
         self._check(self.lib.fx_reset(self._h), "fx_reset")
+
+    def set_sample_rate(self, sample_rate: float):
+        self._check(self.lib.fx_set_sample_rate(self._h, sample_rate), "fx_set_sample_rate")
+
+    def set_track_active(self, track: int, active: bool, reset_state: bool = False):
+        self._check(self.lib.fx_set_track_active(self._h, track, 1 if active else 0, 1 if reset_state else 0), "fx_set_track_active")
+
+    def clear_buffer(self, track: int = -1):
+        self._check(self.lib.fx_clear_buffer(self._h, track), "fx_clear_buffer")
 
     # -- batch analysis, host buffers ------------------------------------------------------------------------
     def analyse_host(self, audio: np.ndarray, want_raw=True, want_smooth=True, want_diag=True):
@@ -241,9 +281,10 @@ class Engine:
         return nf.value
 
     def synth_device(self, d_audio_ptr: int, track_stride: int, n_samples: int, first_track: int = 0, seed: int = 0x5EED,
-                     stream: int | None = None):
-        self._check(self.lib.fx_synth_device(self._h, d_audio_ptr, track_stride, n_samples, first_track, seed, stream),
-                    "fx_synth_device")
+                     stream: int | None = None, first_sample: int = 0):
+        """Synthetic workload: samples [first_sample, first_sample + n_samples) of tracks first_track ..."""
+        self._check(self.lib.fx_synth_device_at(self._h, d_audio_ptr, track_stride, n_samples, first_track, first_sample, seed, stream),
+                    "fx_synth_device_at")
 
     # -- real-time path ----------------------------------------------------------------------------------------
     def push_block(self, block: np.ndarray, first_track: int = 0):
@@ -263,6 +304,38 @@ class Engine:
         idx = c_uint64(0)
         self._check(self.lib.fx_poll_features(self._h, track, out, ctypes.byref(idx)), "fx_poll_features")
         return np.frombuffer(out, dtype=np.float32).copy(), idx.value
+
+    def poll_block(self, first_track: int = 0, n_tracks: int | None = None):
+        n = self.cfg.n_tracks - first_track if n_tracks is None else n_tracks
+        out = np.empty((n, NUM_FEATURES), np.float32)
+        idx = np.zeros(n, np.uint64)
+        self._check(self.lib.fx_poll_block(self._h, first_track, n, out.ctypes.data, idx.ctypes.data), "fx_poll_block")
+        return out, idx
+
+    def rt_start(self, callback=None):
+        """Start the group workers.  callback(first_track, n_tracks, frame_index, n_new) runs on a worker thread."""
+        if callback is not None:
+            self._cb = FEATURES_CALLBACK(lambda user, t0, n, idx, new: callback(t0, n, idx, new))
+            self._check(self.lib.fx_set_features_callback(self._h, self._cb, None), "fx_set_features_callback")
+        self._check(self.lib.fx_rt_start(self._h), "fx_rt_start")
+
+    def rt_stop(self):
+        self._check(self.lib.fx_rt_stop(self._h), "fx_rt_stop")
+
+    def rt_stats(self, reset: bool = False) -> dict:
+        s = RtStats()
+        self._check(self.lib.fx_rt_get_stats(self._h, ctypes.byref(s), 1 if reset else 0), "fx_rt_get_stats")
+        return {k: getattr(s, k) for k, _ in RtStats._fields_}
+
+    def osc_encode(self, tracks, addresses, n_floats: int = 12, stride: int = 128):
+        """One OSC 1.0 datagram per listed track from the latest published vectors: list of bytes."""
+        n = len(tracks)
+        tr = (c_int * n)(*tracks)
+        ad = (c_char_p * n)(*[a.encode() for a in addresses])
+        out = np.zeros((n, stride), np.uint8)
+        sizes = (c_int * n)()
+        self._check(self.lib.fx_osc_encode_tracks(self._h, tr, n, ad, n_floats, out.ctypes.data, stride, sizes), "fx_osc_encode_tracks")
+        return [out[i, : sizes[i]].tobytes() for i in range(n)]
 
     def flush(self):
         self._check(self.lib.fx_flush(self._h), "fx_flush")
@@ -299,6 +372,16 @@ def measure_fp32_peak(device: int = 0) -> float:
     if st != 0:
         raise FxError(f"fx_measure_fp32_peak failed ({st})")
     return tf.value
+
+
+def h2d_probe(device: int = 0, nbytes: int = 1 << 30, reps: int = 4, write_combined: bool = False) -> float:
+    """GB/s of plain pinned -> device cudaMemcpyAsync on `device` (fx_h2d_probe)."""
+    lib = load_library()
+    g = c_double(0)
+    st = lib.fx_h2d_probe(device, nbytes, reps, 1 if write_combined else 0, ctypes.byref(g))
+    if st != 0:
+        raise FxError(f"fx_h2d_probe failed ({st})")
+    return g.value
 
 
 def osc_order(vec12: np.ndarray, n_out: int = 12) -> np.ndarray:

@@ -8,11 +8,13 @@
 // keeps compiling when it switches `#include "include.h"` for this header and `juce::` device plumbing for
 // fxb200::AudioDeviceManager.  What changed underneath:
 //   * AudioDataCollector's 4096-float ring + spinning consumer (AudioDataCollector.h:24,72-94) is the engine's
-//     pinned host ring, streamed to the GPU with cudaMemcpyAsync per track group (fx_push_block / fx_process);
-//   * the two analyser threads per track (AnalyserTrackController.h:184-185) are one GPU launch sequence for
-//     all tracks: startThread / notify / stopThread keep their meaning (start analysing / new data / stop),
-//     but no CPU thread spins;
-//   * AudioFeatures::getValue reads the engine's latest smoothed vector (fx_poll_features).
+//     pinned host ring (fx_push_block on the audio thread: copy + publish + wake, nothing else);
+//   * the two analyser threads per track (AnalyserTrackController.h:184-185) are the engine's worker threads, one
+//     per track group: startThread / stopThread start and stop the analysis of the track, the wake-up that
+//     Thread::notify() gave is part of fx_push_block, and no CPU thread spins;
+//   * AudioFeatures::getValue reads the engine's latest published smoothed vector (fx_poll_features, a seqlock);
+//   * the 60 Hz timers of OSCFeatureAnalysisOutput (OSCFeatureAnalysisOutput.h:84-87,133) share one timer thread
+//     (as juce::Timer objects do) that encodes every sender's datagram in one pass and ships them with sendmmsg.
 // Everything lives in namespace fxb200 so that it can coexist with JUCE.
 #pragma once
 
@@ -21,16 +23,21 @@
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <sys/socket.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -69,9 +76,17 @@ public:
 
 // ------------------------------------------------------------------------------------------------------
 // AudioDeviceManager: stands where juce::AudioDeviceManager stood in AnalyserTrackController's constructor
-// (AnalyserTrackController.h:17,35,41).  It owns the GPU engine for all its input channels.  The host's audio
-// thread calls processBlock() with the device's channel pointers; the manager fans the block out to the
-// registered collectors exactly as JUCE's device manager calls each AudioIODeviceCallback, then wakes the analysis.
+// (AnalyserTrackController.h:17,35,41).  It owns the GPU engine for all its input channels.
+//
+// Threads, as in the reference (AudioDataCollector.h:36-70 copies and notifies; the analysis runs on its own threads,
+// RealTimeAnalyser.h:97-127):
+//   audio thread     processBlock(): every registered collector stages its channel pointer, then ONE fx_push_block per run
+//                    of staged channels copies the block into the pinned ring and wakes the engine's group workers.
+//                    No CUDA call, no lock, no allocation, no exception.
+//   engine workers   analyse the complete hops (started by the first RealTimeAnalyser::startThread, stopped by the last
+//                    stopThread) and then run the after-analysis hooks on the worker thread -- where
+//                    RealTimeSpectralAnalyser::run fires its onset callback (RealTimeAnalyser.h:228-229).
+//   message thread   everything else (construction, parameters, transport events).
 class AudioDeviceManager
 {
 public:
@@ -87,7 +102,7 @@ public:
         cfg.hop = windowSize / 2;                // RealTimeAudioAnalysis.h:207
         cfg.sample_rate = sampleRate;
         cfg.device = device;
-        cfg.tracks_per_group = tracksPerGroup;
+        cfg.tracks_per_group = tracksPerGroup > 0 ? tracksPerGroup : (numInputChannels > 128 ? 128 : numInputChannels);
         cfg.ring_hops = 16;
         setup.bufferSize = bufferSize;
         setup.sampleRate = sampleRate;
@@ -95,9 +110,19 @@ public:
         hopSize = cfg.hop;
         if (fx_engine_create (&cfg, &engine) != FX_OK)
             throw std::runtime_error (String ("fx_engine_create: ") + fx_last_error (nullptr));   // no CPU fallback
+        staged.assign ((size_t) numChannels, nullptr);
+        owners.assign ((size_t) numChannels, nullptr);
+        running.assign ((size_t) numChannels, 0);
+        fresh.assign ((size_t) numChannels, 1);
+        // a channel is analysed once an AnalyserTrackController has claimed it and started its analysers
+        fx_set_track_active (engine, -1, 0, 0);
+        fx_set_features_callback (engine, &AudioDeviceManager::featuresThunk, this);
     }
 
-    ~AudioDeviceManager() { if (engine) fx_engine_destroy (engine); }
+    ~AudioDeviceManager()
+    {
+        if (engine) { fx_rt_stop (engine); fx_engine_destroy (engine); }
+    }
     AudioDeviceManager (const AudioDeviceManager&) = delete;
     AudioDeviceManager& operator= (const AudioDeviceManager&) = delete;
 
@@ -109,64 +134,130 @@ public:
     }
     void getAudioDeviceSetup (AudioDeviceSetup& s) const { s = setup; }
 
-    // The audio thread's entry point: one device block for every channel.  Collectors copy into the pinned ring
-    // and ask for a wake-up (Thread::notify in the reference); the wake-up itself happens once per block.
-    void processBlock (const float** inputChannelData, int numInputChannels, int numSamples)
+    // The audio thread's entry point: one device block for every channel (what JUCE's device manager does when it calls each
+    // AudioIODeviceCallback).  Only copies: the analysis happens on the engine's workers.
+    void processBlock (const float** inputChannelData, int numInputChannels, int numSamples,
+                       float** outputChannelData = nullptr, int numOutputChannels = 0) noexcept
     {
+        inBlock = true;
         for (auto* cb : callbacks)
-            cb->audioDeviceIOCallback (inputChannelData, numInputChannels, nullptr, 0, numSamples);
-        if (wakeRequested)
+            cb->audioDeviceIOCallback (inputChannelData, numInputChannels, outputChannelData, numOutputChannels, numSamples);
+        inBlock = false;
+        for (int c = 0; c < numChannels;)
         {
-            wakeRequested = false;
-            if (pump() > 0)
-                for (auto& h : afterAnalysis) h.second();
+            if (staged[(size_t) c] == nullptr) { ++c; continue; }
+            int end = c;
+            while (end < numChannels && staged[(size_t) end] != nullptr) ++end;
+            const fx_status st = fx_push_block (engine, c, end - c, staged.data() + c, numSamples);
+            if (st != FX_OK) { lastPushStatus = st; ++pushErrors; }
+            for (int k = c; k < end; ++k) staged[(size_t) k] = nullptr;
+            c = end;
         }
     }
-    void requestWake() noexcept { wakeRequested = true; }
-    void addAfterAnalysisHook (const void* owner, std::function<void()> f) { afterAnalysis.emplace_back (owner, std::move (f)); }
+    // collectors (audio thread): inside processBlock the pointer is staged for the block's one push
+    void pushFromCollector (int track, const float* src, int numSamples) noexcept
+    {
+        if (track < 0 || track >= numChannels) return;
+        if (inBlock) { staged[(size_t) track] = src; return; }
+        const float* one[1] = { src };
+        const fx_status st = fx_push_block (engine, track, 1, one, numSamples);
+        if (st != FX_OK) { lastPushStatus = st; ++pushErrors; }
+    }
+    int  getLastPushStatus() const noexcept { return lastPushStatus; }     // FX_ERR_OVERRUN: the analysis fell a whole ring behind
+    long getPushErrorCount() const noexcept { return pushErrors; }
+
+    // hooks run on an engine worker thread after the hops of their track were analysed
+    void addAfterAnalysisHook (const void* owner, int track, std::function<void()> f)
+    {
+        std::lock_guard<std::mutex> lk (hooksMutex);
+        afterAnalysis.push_back (Hook { owner, track, std::move (f) });
+    }
     void removeAfterAnalysisHooks (const void* owner)
     {
+        std::lock_guard<std::mutex> lk (hooksMutex);
         for (size_t i = afterAnalysis.size(); i-- > 0;)
-            if (afterAnalysis[i].first == owner) afterAnalysis.erase (afterAnalysis.begin() + (long) i);
-    }
-
-    // The analysis wake-up (what Thread::notify() led to in the reference).  Returns the number of new hops analysed.
-    long pump()
-    {
-        long n = 0;
-        if (analysing && fx_process (engine, &n) != FX_OK)
-            throw std::runtime_error (String ("fx_process: ") + fx_last_error (engine));
-        return n;
+            if (afterAnalysis[i].owner == owner) afterAnalysis.erase (afterAnalysis.begin() + (long) i);
     }
 
     fx_engine* getEngine() const noexcept { return engine; }
     int getNumInputChannels() const noexcept { return numChannels; }
     long getHopSize() const noexcept { return hopSize; }
-    void setAnalysing (bool on) noexcept { analysing = on; }
+
+    // RealTimeAnalyser::startThread / stopThread (AnalyserTrackController.h:184-185,190-194)
+    void analyserStarted (int track)
+    {
+        if (track < 0 || track >= numChannels) return;
+        std::lock_guard<std::mutex> lk (stateMutex);
+        if (running[(size_t) track]++ == 0)
+        {
+            fx_set_track_active (engine, track, 1, fresh[(size_t) track]);      // a new controller starts from empty histories
+            fresh[(size_t) track] = 0;
+        }
+        if (totalRunning++ == 0) fx_rt_start (engine);
+    }
+    void analyserStopped (int track)
+    {
+        if (track < 0 || track >= numChannels) return;
+        std::lock_guard<std::mutex> lk (stateMutex);
+        if (running[(size_t) track] == 0) return;
+        if (--running[(size_t) track] == 0) fx_set_track_active (engine, track, 0, 0);
+        if (--totalRunning == 0) fx_rt_stop (engine);
+    }
 
     // one collector per track feeds the ring; the reference's second collector per track carries the same samples
     bool claimTrack (int track, const void* owner)
     {
         if (track < 0 || track >= numChannels) return false;
-        if (owners.size() < (size_t) numChannels) owners.resize ((size_t) numChannels, nullptr);
-        if (owners[(size_t) track] == nullptr) owners[(size_t) track] = owner;
+        std::lock_guard<std::mutex> lk (stateMutex);
+        if (owners[(size_t) track] == nullptr) { owners[(size_t) track] = owner; fresh[(size_t) track] = 1; }
         return owners[(size_t) track] == owner;
     }
     void releaseTrack (int track, const void* owner)
     {
-        if (track >= 0 && (size_t) track < owners.size() && owners[(size_t) track] == owner) owners[(size_t) track] = nullptr;
+        if (track < 0 || track >= numChannels) return;
+        std::lock_guard<std::mutex> lk (stateMutex);
+        if (owners[(size_t) track] == owner) owners[(size_t) track] = nullptr;
+    }
+
+    // blocks until `track` has analysed at least `hop` hops (tests and offline drivers; never the audio thread)
+    bool waitForHop (int track, uint64_t hop, int timeoutMs = 5000) const
+    {
+        float v[FX_NUM_FEATURES];
+        uint64_t idx = 0;
+        for (int waited = 0; waited <= timeoutMs * 20; ++waited)
+        {
+            if (fx_poll_features (engine, track, v, &idx) == FX_OK && idx >= hop) return true;
+            ::usleep (50);
+        }
+        return false;
     }
 
 private:
+    struct Hook { const void* owner; int track; std::function<void()> fn; };
+
+    static void featuresThunk (void* user, int firstTrack, int nTracks, uint64_t /*frameIndex*/, int /*nNew*/)
+    {
+        auto* self = static_cast<AudioDeviceManager*> (user);
+        std::lock_guard<std::mutex> lk (self->hooksMutex);
+        for (auto& h : self->afterAnalysis)
+            if (h.track >= firstTrack && h.track < firstTrack + nTracks) h.fn();
+    }
+
     fx_engine* engine = nullptr;
     AudioDeviceSetup setup;
     int numChannels = 0;
     long hopSize = 0;
-    bool analysing = true;
-    bool wakeRequested = false;
-    std::vector<std::pair<const void*, std::function<void()>>> afterAnalysis;
+    bool inBlock = false;
+    int lastPushStatus = FX_OK;
+    long pushErrors = 0;
+    int totalRunning = 0;
+    std::mutex stateMutex, hooksMutex;
+    std::vector<Hook> afterAnalysis;
     std::vector<AudioIODeviceCallback*> callbacks;
+    std::vector<const float*> staged;
     std::vector<const void*> owners;
+    std::vector<int> running;
+    std::vector<int> fresh;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -193,8 +284,11 @@ struct AudioFeatures
         for (int f = 0; f < numFeatures; ++f)
             local.emplace_back ((f == enOnset || f == enFlux) ? 1 : 10);      // RealTimeAnalyser.h:72-73
     }
+    AudioFeatures (fx_engine* e, int trackIndex) : AudioFeatures() { engine = e; track = trackIndex; }
 
     void bind (fx_engine* e, int trackIndex) { engine = e; track = trackIndex; }
+    fx_engine* getEngine() const noexcept { return engine; }
+    int getTrack() const noexcept { return track; }
 
     void updateFeature (eAudioFeature f, float v)                              // RealTimeAnalyser.h:76-82
     {
@@ -243,7 +337,7 @@ public:
 
     void attach (AudioDeviceManager& m) { manager = &m; primary = m.claimTrack (channelToCollect, this); }
 
-    // Audio thread.  Wait-free: a memcpy into the pinned ring and an index publish (fx_push_block).
+    // Audio thread.  Wait-free: the block is staged for the manager's one fx_push_block (memcpy into the pinned ring + publish).
     void audioDeviceIOCallback (const float** inputChannelData, int numInputChannels,
                                 float** outputChannelData, int numOutputChannels, int numberOfSamples) override
     {
@@ -251,11 +345,7 @@ public:
         const int available = collectInput ? numInputChannels : numOutputChannels;
         if (channelData == nullptr || channelToCollect < 0 || channelToCollect >= available || manager == nullptr) return;
         const float* src = channelData[channelToCollect];
-        if (primary)
-        {
-            const float* one[1] = { src };
-            lastStatus = fx_push_block (manager->getEngine(), channelToCollect, 1, one, numberOfSamples);
-        }
+        if (primary) manager->pushFromCollector (channelToCollect, src, numberOfSamples);
         if (bufferToDrawUpdated)                                                                       // :96-102
         {
             AudioSampleBuffer b (1, numberOfSamples);
@@ -268,9 +358,10 @@ public:
     void setBufferToDrawUpdatedCallback  (std::function<void (AudioSampleBuffer&)> f) { bufferToDrawUpdated = std::move (f); }
     void setNotifyAnalysisThreadCallback (std::function<void()> f)                    { notifyAnalysisThread = std::move (f); }
 
-    void toggleCollectInput (bool shouldCollectInput) noexcept { clearBuffer(); collectInput = shouldCollectInput; }   // :119
+    void toggleCollectInput (bool shouldCollectInput) { clearBuffer(); collectInput = shouldCollectInput; }         // :119
     void setExpectedSamplesPerBlock (int spb) noexcept         { expectedSamplesPerBlock = spb; }                    // :120
-    void clearBuffer() {}                          // :122 -- the pinned ring only ever exposes samples that were pushed
+    // :122 circleBuffer.clear(): what was collected but not analysed yet becomes silence, positions stay
+    void clearBuffer() { if (manager && primary) fx_clear_buffer (manager->getEngine(), channelToCollect); }
     void setChannelToCollect (int c)
     {
         if (manager) manager->releaseTrack (channelToCollect, this);
@@ -283,7 +374,8 @@ public:
         if (manager) fx_set_gain (manager->getEngine(), channelToCollect, g);
     }
     int  getChannel() const noexcept   { return channelToCollect; }
-    int  getLastStatus() const noexcept { return lastStatus; }      // FX_ERR_OVERRUN when the analysis fell behind the producer
+    int  getLastStatus() const noexcept { return manager ? manager->getLastPushStatus() : FX_OK; }   // FX_ERR_OVERRUN when the analysis fell behind the producer
+    bool isPrimary() const noexcept { return primary; }
     AudioDeviceManager* getManager() const noexcept { return manager; }
 
 private:
@@ -295,7 +387,6 @@ private:
     int channelToCollect = 0;
     bool collectInput = true;
     bool primary = false;
-    int lastStatus = FX_OK;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -314,19 +405,33 @@ class RealTimeAnalyser
 public:
     RealTimeAnalyser (AudioDataCollector& adc, AudioFeatures& featuresRef, int windowSize, double sampleRate = 48000.0)
         : audioDataCollector (adc), features (featuresRef), window (windowSize), rate (sampleRate) {}
-    virtual ~RealTimeAnalyser() = default;
+    virtual ~RealTimeAnalyser() { stopThread (0); }
     RealTimeAnalyser (const RealTimeAnalyser&) = delete;
     RealTimeAnalyser& operator= (const RealTimeAnalyser&) = delete;
 
-    void sampleRateChanged (double newSampleRate) { rate = newSampleRate; }      // :111-114 (the engine's rate is fixed at creation)
-    void startThread (int /*priority*/ = 5)       { running = true; }
-    bool stopThread (int /*timeoutMs*/)           { running = false; return true; }
-    bool isThreadRunning() const noexcept         { return running; }
-    // new audio has arrived: ask the manager to analyse whatever hops are complete (all tracks at once, once per block)
-    void notify()
+    // :111-114 fft.setNyquistValue: every frequency-dependent quantity follows from the next analysed hop on (one rate per
+    // device manager, as one audio device has)
+    void sampleRateChanged (double newSampleRate)
     {
-        if (running && audioDataCollector.getManager() != nullptr) audioDataCollector.getManager()->requestWake();
+        rate = newSampleRate;
+        if (fx_engine* e = engineOrNull()) fx_set_sample_rate (e, newSampleRate);
     }
+    void startThread (int /*priority*/ = 5)
+    {
+        if (running) return;
+        running = true;
+        if (auto* m = audioDataCollector.getManager()) m->analyserStarted (audioDataCollector.getChannel());
+    }
+    bool stopThread (int /*timeoutMs*/)
+    {
+        if (! running) return true;
+        running = false;
+        if (auto* m = audioDataCollector.getManager()) m->analyserStopped (audioDataCollector.getChannel());
+        return true;
+    }
+    bool isThreadRunning() const noexcept         { return running; }
+    // Thread::notify(): the wake-up is part of fx_push_block (a futex wake of the group's worker when a hop completed)
+    void notify() {}
     AudioFeatures& getFeatures() { return features; }
     int getWindowSize() const noexcept { return window; }
     double getSampleRate() const noexcept { return rate; }
@@ -368,7 +473,8 @@ public:
     }
     void setOnsetDetectedCallback (std::function<void()> f) { onsetDetectedCallback = std::move (f); }     // :256
 
-    // call after notify(): fires the callback when the newest hop carries an onset (:228-229)
+    // runs on the engine's worker thread after this track's hops were analysed: fires the callback when the newest hop
+    // carries an onset (:228-229)
     void dispatchOnsetCallback()
     {
         if (onsetDetectedCallback && features.getValue (AudioFeatures::enOnset) > 0.0f) onsetDetectedCallback();
@@ -389,27 +495,114 @@ private:
 // ------------------------------------------------------------------------------------------------------
 // OSCFeatureAnalysisOutput (OSCFeatureAnalysisOutput.h:25-145): OSC 1.0 message over UDP,
 // address pattern = bundleAddress, type tags ",ffffffffffff", twelve big-endian floats in the order of :107.
+// connectToAddress starts the 60 Hz timer as the reference does (:133).  All timers share one thread (OSCTimerThread, as
+// juce::Timer objects share JUCE's timer thread): per tick it encodes the datagrams of every running sender in one pass over
+// the engine's published feature block (fx_osc_encode_tracks) and ships them with one sendmmsg per 1024 datagrams.
+class OSCFeatureAnalysisOutput;
+
+class OSCTimerThread
+{
+public:
+    static OSCTimerThread& instance() { static OSCTimerThread t; return t; }
+
+    void add (OSCFeatureAnalysisOutput* o, int hz)
+    {
+        std::lock_guard<std::mutex> lk (mutex);
+        for (auto* x : outputs) if (x == o) return;
+        outputs.push_back (o);
+        rateHz = hz > 0 ? hz : 60;
+        if (! thread.joinable()) { quit = false; thread = std::thread ([this] { run(); }); }
+    }
+    void remove (OSCFeatureAnalysisOutput* o)
+    {
+        std::unique_lock<std::mutex> lk (mutex);
+        for (size_t i = 0; i < outputs.size(); ++i)
+            if (outputs[i] == o) { outputs.erase (outputs.begin() + (long) i); break; }
+        if (outputs.empty() && thread.joinable())
+        {
+            quit = true;
+            lk.unlock();
+            thread.join();
+        }
+    }
+    // one timer tick for every registered sender, on the calling thread; returns the number of datagrams handed to the kernel
+    long tick();
+    unsigned long ticks() const noexcept { return tickCount; }
+    unsigned long datagramsSent() const noexcept { return sentCount; }
+
+    ~OSCTimerThread() { if (thread.joinable()) { quit = true; thread.join(); } }
+
+private:
+    OSCTimerThread() = default;
+    void run()
+    {
+        auto next = std::chrono::steady_clock::now();
+        while (! quit)
+        {
+            next += std::chrono::nanoseconds (1000000000L / rateHz);
+            tick();
+            std::this_thread::sleep_until (next);
+        }
+    }
+
+    std::mutex mutex;
+    std::vector<OSCFeatureAnalysisOutput*> outputs;
+    std::thread thread;
+    std::atomic<bool> quit { false };
+    int rateHz = 60;
+    int sock = -1;
+    std::atomic<unsigned long> tickCount { 0 }, sentCount { 0 };
+    // per-tick scratch (only the ticking thread touches it, under `mutex`)
+    std::vector<int> tracks;
+    std::vector<const char*> addrs;
+    std::vector<unsigned char> wire;
+    std::vector<int> sizes;
+    std::vector<mmsghdr> msgs;
+    std::vector<iovec> iov;
+    std::vector<OSCFeatureAnalysisOutput*> batch;
+};
+
 class OSCFeatureAnalysisOutput
 {
 public:
+    static constexpr int kDatagramStride = 256;
+
     OSCFeatureAnalysisOutput (AudioFeatures& rta, String ip, String bundle)
         : realTimeAudioFeatures (rta), address (std::move (ip)), bundleAddress (std::move (bundle))
     {
         if (! bundleAddress.empty()) connectToAddress (address);                  // :80-81
     }
-    ~OSCFeatureAnalysisOutput() { if (sock >= 0) ::close (sock); }
+    ~OSCFeatureAnalysisOutput() { stopTimer(); if (sock >= 0) ::close (sock); }
     OSCFeatureAnalysisOutput (const OSCFeatureAnalysisOutput&) = delete;
     OSCFeatureAnalysisOutput& operator= (const OSCFeatureAnalysisOutput&) = delete;
 
-    void timerCallback() { sendSpectralFeaturesViaOSC (true); }                   // :84-87 (60 Hz in the reference, :133)
+    // drivers that step the sender by hand switch the automatic 60 Hz timer off before constructing senders
+    static bool& timerAutoStart() { static bool on = true; return on; }
+
+    void startTimerHz (int hz) { timerRunning = true; OSCTimerThread::instance().add (this, hz); }          // juce::Timer
+    void stopTimer()           { if (timerRunning) { timerRunning = false; OSCTimerThread::instance().remove (this); } }
+    bool isTimerRunning() const noexcept { return timerRunning; }
+
+    void timerCallback() { sendSpectralFeaturesViaOSC (true); }                   // :84-87
 
     // builds the message; returns the bytes that went (or would go) on the wire
     std::vector<uint8_t> encode() const
     {
+        std::vector<uint8_t> m ((size_t) kDatagramStride);
+        int size = 0;
+        if (fx_engine* e = realTimeAudioFeatures.getEngine())
+        {
+            const int track = realTimeAudioFeatures.getTrack();
+            const char* a = bundleAddress.c_str();
+            fx_osc_encode_tracks (e, &track, 1, &a, FX_OSC_FLOATS_CODE, m.data(), kDatagramStride, &size);
+            m.resize ((size_t) size);
+            return m;
+        }
+        // unbound feature store: the same message from the host-side histories
         float v[FX_NUM_FEATURES], o[FX_OSC_FLOATS_CODE];
         for (int f = 0; f < FX_NUM_FEATURES; ++f) v[f] = realTimeAudioFeatures.getValue ((AudioFeatures::eAudioFeature) f);
         fx_osc_order (v, o, FX_OSC_FLOATS_CODE);
-        std::vector<uint8_t> m;
+        m.clear();
         auto padded = [&m] (const String& s)
         {
             m.insert (m.end(), s.begin(), s.end());
@@ -442,14 +635,18 @@ public:
         const size_t sep = newAddress.find_last_of (':');
         if (sep != String::npos) port = std::atoi (newAddress.substr (sep + 1).c_str());
         address = newAddress.substr (0, newAddress.find (':'));
+        stopTimer();
         if (sock >= 0) { ::close (sock); sock = -1; }
+        connected = false;
         addrinfo hints{}; hints.ai_family = AF_INET; hints.ai_socktype = SOCK_DGRAM;
         addrinfo* res = nullptr;
         if (getaddrinfo (address.c_str(), std::to_string (port).c_str(), &hints, &res) != 0 || res == nullptr) return false;
         sock = ::socket (res->ai_family, res->ai_socktype, res->ai_protocol);
         const bool ok = sock >= 0 && ::connect (sock, res->ai_addr, res->ai_addrlen) == 0;
+        if (ok && res->ai_addrlen <= sizeof (destination)) { std::memcpy (&destination, res->ai_addr, res->ai_addrlen); destinationLen = res->ai_addrlen; connected = true; }
         freeaddrinfo (res);
         if (! ok && sock >= 0) { ::close (sock); sock = -1; }
+        if (ok && timerAutoStart()) startTimerHz (60);                            // :133
         return ok;
     }
 
@@ -460,8 +657,73 @@ public:
     String bundleAddress { "/Audio/Features" };
 
 private:
+    friend class OSCTimerThread;
     int sock = -1;
+    bool connected = false, timerRunning = false;
+    sockaddr_storage destination{};
+    socklen_t destinationLen = 0;
 };
+
+inline long OSCTimerThread::tick()
+{
+    std::lock_guard<std::mutex> lk (mutex);
+    ++tickCount;
+    if (outputs.empty()) return 0;
+    if (sock < 0) sock = ::socket (AF_INET, SOCK_DGRAM, 0);
+    const size_t stride = (size_t) OSCFeatureAnalysisOutput::kDatagramStride;
+    long sent = 0;
+    // senders bound to an engine, engine by engine: one encode pass each
+    std::vector<OSCFeatureAnalysisOutput*> pending (outputs);
+    while (! pending.empty())
+    {
+        fx_engine* e = pending.front()->realTimeAudioFeatures.getEngine();
+        batch.clear(); tracks.clear(); addrs.clear();
+        for (size_t i = 0; i < pending.size();)
+        {
+            OSCFeatureAnalysisOutput* o = pending[i];
+            if (o->realTimeAudioFeatures.getEngine() != e) { ++i; continue; }
+            if (o->connected) { batch.push_back (o); tracks.push_back (o->realTimeAudioFeatures.getTrack()); addrs.push_back (o->bundleAddress.c_str()); }
+            pending.erase (pending.begin() + (long) i);
+        }
+        if (batch.empty()) continue;
+        const size_t n = batch.size();
+        wire.resize (n * stride); sizes.assign (n, 0);
+        if (e != nullptr)
+        {
+            if (fx_osc_encode_tracks (e, tracks.data(), (int) n, addrs.data(), FX_OSC_FLOATS_CODE, wire.data(), (int) stride, sizes.data()) != FX_OK) continue;
+        }
+        else
+            for (size_t i = 0; i < n; ++i)
+            {
+                const std::vector<uint8_t> m = batch[i]->encode();
+                sizes[i] = (int) (m.size() <= stride ? m.size() : 0);
+                std::memcpy (wire.data() + i * stride, m.data(), (size_t) sizes[i]);
+            }
+        msgs.assign (n, mmsghdr{}); iov.resize (n);
+        size_t count = 0;
+        for (size_t i = 0; i < n; ++i)
+        {
+            if (sizes[i] <= 0) continue;
+            iov[count].iov_base = wire.data() + i * stride;
+            iov[count].iov_len = (size_t) sizes[i];
+            msgs[count].msg_hdr.msg_name = &batch[i]->destination;
+            msgs[count].msg_hdr.msg_namelen = batch[i]->destinationLen;
+            msgs[count].msg_hdr.msg_iov = &iov[count];
+            msgs[count].msg_hdr.msg_iovlen = 1;
+            ++count;
+        }
+        for (size_t at = 0; at < count;)
+        {
+            const size_t chunk = count - at < 1024 ? count - at : 1024;         // UIO_MAXIOV
+            const int r = ::sendmmsg (sock, msgs.data() + at, (unsigned) chunk, 0);
+            if (r <= 0) break;
+            sent += r;
+            at += (size_t) r;
+        }
+    }
+    sentCount += (unsigned long) sent;
+    return sent;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // AudioFormatReader: what AudioFormatManager::createReaderFor (AudioFilePlayer.h:47, after registerBasicFormats :17) yields
@@ -663,7 +925,8 @@ class AnalyserTrackController
 public:
     AnalyserTrackController (AudioDeviceManager& deviceManagerRef, int channelToAnalyse, String nameOfInputChannel,
                              String ip, String secondaryIP, String bundle)
-        : audioDataCollectorHarm (channelToAnalyse), audioDataCollectorSpec (channelToAnalyse),
+        : features (channelToAnalyse >= 0 ? deviceManagerRef.getEngine() : nullptr, channelToAnalyse),
+          audioDataCollectorHarm (channelToAnalyse), audioDataCollectorSpec (channelToAnalyse),
           audioAnalyserHarm (audioDataCollectorHarm, features, 2048), audioAnalyserSpec (audioDataCollectorSpec, features, 2048),
           oscFeatureSender (features, std::move (ip), bundle), secondaryOSCFeatureSender (features, std::move (secondaryIP), bundle),
           deviceManager (deviceManagerRef), channelName (std::move (nameOfInputChannel))
@@ -671,14 +934,13 @@ public:
         enabled = channelToAnalyse >= 0;                                          // :27
         if (enabled)
         {
-            features.bind (deviceManager.getEngine(), channelToAnalyse);
             audioDataCollectorSpec.attach (deviceManager);                        // feeds the ring
             audioDataCollectorHarm.attach (deviceManager);                        // same samples: second collector of the reference (:35)
             audioDataCollectorHarm.setNotifyAnalysisThreadCallback ([this]() { audioAnalyserHarm.notify(); });
             deviceManager.addAudioCallback (&audioDataCollectorHarm);
             audioDataCollectorSpec.setNotifyAnalysisThreadCallback ([this]() { audioAnalyserSpec.notify(); });
             deviceManager.addAudioCallback (&audioDataCollectorSpec);
-            deviceManager.addAfterAnalysisHook (this, [this]() { audioAnalyserSpec.dispatchOnsetCallback(); });      // RealTimeAnalyser.h:228-229
+            deviceManager.addAfterAnalysisHook (this, channelToAnalyse, [this]() { audioAnalyserSpec.dispatchOnsetCallback(); });      // RealTimeAnalyser.h:228-229
         }
     }
 

@@ -75,7 +75,7 @@ typedef struct fx_config {
     float  onset_multiplier;    /* meanThresholdMultiplier, SpectralCharacteristics.h:311, default 1.7 */
     float  gain;                /* AudioDataCollector::setGain (AudioDataCollector.h:124), default 1 */
     long   max_frames_per_call; /* capacity of the engine-owned device result buffers (frames per track per call) */
-    int    ring_hops;           /* streaming: device + pinned ring length in hops per track (>= window/hop + 2) */
+    int    ring_hops;           /* streaming: device + pinned ring length in hops per track (>= window/hop + 2); 0 = no real-time path */
     int    tracks_per_group;    /* streaming: tracks per CUDA stream / pinned-ring group; 0 = all tracks in one group */
 } fx_config;
 
@@ -87,7 +87,9 @@ fx_status   fx_engine_destroy (fx_engine* e);
 const char* fx_last_error     (const fx_engine* e);      /* e may be NULL: last create error */
 const char* fx_version        (void);
 
-/* Runtime parameter surface (applies from the next analysed frame).
+/* Runtime parameter surface (applies from the next analysed hop; a gain change keeps the older part of the overlapped
+ * window at the gain it was collected with, as AudioDataCollector::getAnalysisBuffer applies it on the way out of the
+ * ring, AudioDataCollector.h:88).
  * AudioDataCollector::setGain (AudioDataCollector.h:124);
  * RealTimeSpectralAnalyser::setOnsetDetectionType / setOnsetWindowLength / setOnsetDetectionSensitivity
  * (RealTimeAnalyser.h:244-258; multiplier = 1 + sensitivity).  track = -1 applies to every track.
@@ -142,18 +144,78 @@ fx_status   fx_decode_pcm_device (fx_engine* e, const void* d_pcm, int format, i
                                   float* d_audio, long audio_stride, void* stream);
 
 /* ---- real-time path --------------------------------------------------------------------------------
- * fx_push_block replaces AudioDataCollector::audioDeviceIOCallback (AudioDataCollector.h:36-70) for a
- * range of tracks: copies n_samples of each channel into the pinned host ring (wait-free: memcpy + index
- * publish; no allocation, no CUDA call).  channels[i] is track first_track + i.
- * fx_process replaces the analyser threads' wake-up (RealTimeAnalyser.h:141-177, :201-234): streams the
- * new samples to the device (cudaMemcpyAsync on the group's stream), analyses every hop that became
- * complete and brings the smoothed features back to host memory.  Returns the number of new frames per
- * track in *n_new_frames (may be 0).  fx_poll_features replaces AudioFeatures::getValue x 12 as read by the
- * OSC / GUI timers (OSCFeatureAnalysisOutput.h:91-104): lock-free snapshot of the latest smoothed vector. */
+ * Threading contract (the reference: AudioDataCollector.h:36-70 only copies and notifies, the
+ * analysis runs on two juce::Threads per track, RealTimeAnalyser.h:97-127, AnalyserTrackController.h:184-185):
+ *
+ *   audio thread      fx_push_block ONLY.  Wait-free: bounds check, memcpy into the pinned ring, one atomic publish per
+ *                     track and -- when a hop became complete and the group's worker is asleep -- one futex wake.  No lock,
+ *                     no allocation, no CUDA call.  One producer thread per track at a time.
+ *   worker threads    one per track group, inside the engine (fx_rt_start / fx_rt_stop): sleeps until a hop is complete on
+ *                     every ACTIVE track of its group, streams the new samples to the device (cudaMemcpyAsync on the
+ *                     group's stream), analyses them, brings the smoothed vectors back and publishes them under a
+ *                     seqlock; then calls the features callback.  Groups advance independently of each other.
+ *   any other thread  fx_poll_features / fx_poll_block / fx_osc_encode_tracks (lock-free snapshots, never torn);
+ *                     the parameter calls fx_set_gain / fx_set_onset / fx_set_sample_rate / fx_set_track_active /
+ *                     fx_clear_buffer / fx_reset (they take the affected groups' batch mutex, i.e. they are applied
+ *                     between two batches = at a hop boundary; the audio thread never touches that mutex).
+ *
+ * Every device and host buffer of this path is sized at fx_engine_create for ring_hops hops: the steady state performs no
+ * allocation and no device-wide synchronisation.  ring_hops = 0 creates the engine without the real-time path.
+ *
+ * fx_push_block replaces AudioDataCollector::audioDeviceIOCallback (AudioDataCollector.h:36-70) for a range of tracks;
+ * channels[i] is track first_track + i.  FX_ERR_OVERRUN: a block did not fit (the analysis fell behind by a whole ring);
+ * NOTHING of the call was copied, the overrun is counted (fx_rt_stats) and the tracks stay in step.  Blocks for inactive
+ * tracks are dropped.
+ * fx_process is the synchronous form of one worker pass over every group, on the calling thread -- a test hook and the
+ * way to drive the engine without worker threads; it must not be called while the workers run (FX_ERR_INVALID_ARG).
+ * fx_poll_features replaces AudioFeatures::getValue x 12 as read by the OSC / GUI timers (OSCFeatureAnalysisOutput.h:91-104). */
 fx_status   fx_push_block    (fx_engine* e, int first_track, int n_tracks, const float* const* channels, int n_samples);
 fx_status   fx_process       (fx_engine* e, long* n_new_frames);
 fx_status   fx_poll_features (fx_engine* e, int track, float out12[FX_NUM_FEATURES], uint64_t* frame_index);
+/* the same for a range of tracks in one call: out [n_tracks][12], frame_index [n_tracks] (may be NULL) */
+fx_status   fx_poll_block    (fx_engine* e, int first_track, int n_tracks, float* out, uint64_t* frame_index);
 fx_status   fx_flush         (fx_engine* e);             /* synchronise every group stream */
+
+/* juce::Thread::startThread / stopThread of the analysers (AnalyserTrackController.h:184-185,190-194) for the whole engine:
+ * start the group workers / stop and join them (idempotent). */
+fx_status   fx_rt_start      (fx_engine* e);
+fx_status   fx_rt_stop       (fx_engine* e);
+/* Called on a worker thread after the features of `n_new` hops of tracks [first_track, first_track + n_tracks) were
+ * published (frame_index = hops analysed so far in that group) -- where RealTimeSpectralAnalyser::run fires its
+ * onsetDetectedCallback (RealTimeAnalyser.h:228-229).  Set it before fx_rt_start. */
+typedef void (*fx_features_callback) (void* user, int first_track, int n_tracks, uint64_t frame_index, int n_new);
+fx_status   fx_set_features_callback (fx_engine* e, fx_features_callback cb, void* user);
+/* A track is what one AnalyserTrackController owns (AnalyserTrackController.h:17-45).  Only active tracks gate their
+ * group's progress; an inactive track is fed silence.  Activating with reset_state != 0 gives the track the state of a
+ * freshly constructed controller (zero overlap buffer, zero previous spectrum, empty feature / onset histories) starting at
+ * the group's current hop.  All tracks are active after fx_engine_create.  track = -1: every track. */
+fx_status   fx_set_track_active (fx_engine* e, int track, int active, int reset_state);
+/* AudioDataCollector::clearBuffer (AudioDataCollector.h:122, fired by play / pause / stop / file drop,
+ * AnalyserTrackController.h:131-133,167-171, and by toggleCollectInput :119): the samples pushed but not analysed yet
+ * (and the rest of the ring) become zeros; positions do not move. */
+fx_status   fx_clear_buffer  (fx_engine* e, int track);
+/* RealTimeAnalyser::sampleRateChanged -> FFTAnalyser::setNyquistValue (RealTimeAnalyser.h:111-114, called for both
+ * analysers on every prepareToPlay, AnalyserTrackController.h:178-179): every frequency-dependent quantity (bin
+ * frequencies, f0 = 2 nyquist / lag, the harmonic bin tables) follows from the next analysed hop on. */
+fx_status   fx_set_sample_rate (fx_engine* e, double sample_rate);
+
+typedef struct fx_rt_stats {
+    uint64_t batches;            /* worker passes that analysed at least one hop (all groups) */
+    uint64_t hops;               /* hops analysed (summed over groups) */
+    uint64_t overruns;           /* fx_push_block calls refused */
+    double   batch_ms_mean;      /* wake-up -> features published, per batch */
+    double   batch_ms_max;
+} fx_rt_stats;
+fx_status   fx_rt_get_stats  (fx_engine* e, fx_rt_stats* out, int reset);
+
+/* ---- OSC wire output (OSCFeatureAnalysisOutput.h:89-113) -----------------------------------------------
+ * Batch encoder: for each listed track one complete OSC 1.0 message -- address pattern addresses[i] (the reference's
+ * bundleAddress, "/Audio/A<n>", MainComponent.cpp:170), type tags ",f" x n_floats, n_floats big-endian floats of the latest
+ * published vector in the order of :107 (n_floats = 12) or README.md:55-57 (10) -- written at out + i * datagram_stride;
+ * sizes[i] receives its length (0 when it would not fit the stride).  One pass over the published block; the caller sends
+ * the datagrams (the facade: one sendmmsg per 60 Hz tick). */
+fx_status   fx_osc_encode_tracks (fx_engine* e, const int* tracks, int n_tracks, const char* const* addresses, int n_floats,
+                                  unsigned char* out, int datagram_stride, int* sizes);
 
 /* OSC argument order (OSCFeatureAnalysisOutput.h:107): reorder one 12-slot feature vector.
  * n_out = 12 (as the code sends) or 10 (as README.md:55-57 documents). */
@@ -165,6 +227,10 @@ fx_status   fx_osc_order (const float in12[FX_NUM_FEATURES], float* out, int n_o
  * silence / burst insertions.  first_track offsets the track index (multi-GPU sharding by track range). */
 fx_status   fx_synth_device (fx_engine* e, float* d_audio, long track_stride, long n_samples,
                              long first_track, uint64_t seed, void* stream);
+/* the same for samples [first_sample, first_sample + n_samples) of every track: the generator is a pure function of
+ * (seed, track, sample index), so a long stream can be produced slab by slab without a seam */
+fx_status   fx_synth_device_at (fx_engine* e, float* d_audio, long track_stride, long n_samples,
+                                long first_track, long first_sample, uint64_t seed, void* stream);
 /* number of kernels this engine has launched since creation */
 uint64_t    fx_kernel_launches (const fx_engine* e);
 /* Per-kernel device timing: when enabled, every call brackets the analysis kernel (k_analyse) and the small
@@ -174,6 +240,9 @@ fx_status   fx_profile_enable (fx_engine* e, int on);
 fx_status   fx_profile_read   (fx_engine* e, double* ms_analyse, double* ms_post, long* n_calls);
 /* FP32 FMA microbenchmark (registers only) for the compute roofline denominator: achieved TFLOP/s on `device`. */
 fx_status   fx_measure_fp32_peak (int device, double* tflops);
+/* Host -> device link probe: `reps` cudaMemcpyAsync of `bytes` from a pinned (optionally write-combined) host buffer,
+ * GB/s by CUDA events.  Run on every rank at once it measures the box's concurrent upload ceiling. */
+fx_status   fx_h2d_probe (int device, long bytes, int reps, int write_combined, double* gbs);
 
 #ifdef __cplusplus
 }

@@ -2,10 +2,12 @@
 // Written the way an application uses the reference classes: one AnalyserTrackController per input channel on a
 // device manager (MainComponent.cpp:137-171), audio arriving in device blocks, features read back per track.
 // Usage: facade_driver <audio.f32> <n_tracks> <n_samples> <block> <sample_rate> <out.f32> [osc_port]
-// Reads [n_tracks][n_samples] fp32, feeds it in `block`-sample device blocks, and after every block that completed
-// at least one hop appends [hop index, 12 features] x n_tracks to out.f32.
+// Reads [n_tracks][n_samples] fp32, feeds it in `block`-sample device blocks from this ("audio") thread -- processBlock only
+// copies -- and after every block that completed a hop waits until the engine's workers have published it, then appends
+// [hop index, 12 features] x n_tracks to out.f32.  Onset callbacks arrive on the worker threads.
 #include "../../feature-extractor_b200/host/FeatureExtractorB200.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -25,9 +27,10 @@ int main (int argc, char** argv)
     fclose (f);
     FILE* out = fopen (argv[6], "wb");
 
-    AudioDeviceManager deviceManager (T, sr, block, 2048);
+    OSCFeatureAnalysisOutput::timerAutoStart() = false;          // this driver steps the senders by hand, hop by hop
+    AudioDeviceManager deviceManager (T, sr, block, 2048, 0, T > 2 ? 2 : T);      // several track groups
     std::vector<std::unique_ptr<AnalyserTrackController>> tracks;
-    int onsetCallbacks = 0;
+    std::atomic<int> onsetCallbacks { 0 };
     const String osc = argc > 7 ? String ("127.0.0.1:") + argv[7] : String ("127.0.0.1:9000");
     for (int ch = 0; ch < T; ++ch)
     {
@@ -41,16 +44,19 @@ int main (int argc, char** argv)
 
     std::vector<const float*> chans ((size_t) T);
     uint64_t lastHop = 0;
+    const long hopSize = deviceManager.getHopSize();
     for (long pos = 0; pos + block <= S; pos += block)
     {
         for (int ch = 0; ch < T; ++ch) chans[(size_t) ch] = audio.data() + (size_t) ch * (size_t) S + pos;
         deviceManager.processBlock (chans.data(), T, block);
         float v[FX_NUM_FEATURES];
         uint64_t hop = 0;
-        tracks[0]->getFeatures().snapshot (v, &hop);
-        if (hop != lastHop)
+        const uint64_t due = (uint64_t) ((pos + block) / hopSize);
+        if (due != lastHop)
         {
-            lastHop = hop;
+            for (int ch = 0; ch < T; ++ch)
+                if (! deviceManager.waitForHop (ch, due)) { fprintf (stderr, "hop %llu of track %d never arrived\n", (unsigned long long) due, ch); return 4; }
+            lastHop = due;
             for (int ch = 0; ch < T; ++ch)
             {
                 tracks[(size_t) ch]->getFeatures().snapshot (v, &hop);
@@ -68,6 +74,8 @@ int main (int argc, char** argv)
     }
     fclose (out);
     const std::vector<uint8_t> msg = tracks[0]->getOSCSender().encode();
-    printf ("hops %llu onset_callbacks %d osc_bytes %zu\n", (unsigned long long) lastHop, onsetCallbacks, msg.size());
+    for (auto& t : tracks) t->stopAnalysis();
+    printf ("hops %llu onset_callbacks %d osc_bytes %zu push_errors %ld\n", (unsigned long long) lastHop, onsetCallbacks.load(), msg.size(),
+            deviceManager.getPushErrorCount());
     return 0;
 }

@@ -166,6 +166,70 @@ def make_tracks(n_tracks: int, n_samples: int, sr: float, first_track: int = 0, 
 
 
 # ---------------------------------------------------------------------------------------------------------
+# The bench workload, bit-identical to the GPU's generator (feature-extractor_b200/csrc/fx_post.cu:
+# k_synth): Philox-4x32-10 keyed by seed ^ track, counter = sample index / 4; a sine from IEEE double adds and multiplies
+# only.  The reference arm of bench.py and the CPU baseline are fed from here, the GPU arm from k_synth.
+def _philox4x32_10(counter: np.ndarray, key: int) -> np.ndarray:
+    """counter: uint64 array of block indices -> uint32 array [..., 4]"""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    c0 = counter & mask
+    c1 = counter >> np.uint64(32)
+    c2 = np.zeros_like(c0)
+    c3 = np.zeros_like(c0)
+    k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
+
+
+def _synth_sin_turns(r: np.ndarray) -> np.ndarray:
+    q = np.floor(4.0 * r + 0.5)
+    z = r - 0.25 * q
+    a = z * 6.283185307179586
+    a2 = a * a
+    ps = np.full_like(a, -2.505210838544172e-08)
+    for c in (2.755731922398589e-06, -1.984126984126984e-04, 8.333333333333333e-03, -1.666666666666667e-01, 1.0):
+        ps = ps * a2 + c
+    sn = a * ps
+    pc = np.full_like(a, -2.755731922398589e-07)
+    for c in (2.480158730158730e-05, -1.388888888888889e-03, 4.166666666666666e-02, -0.5, 1.0):
+        pc = pc * a2 + c
+    qi = q.astype(np.int64) & 3
+    return np.where(qi == 0, sn, np.where(qi == 1, pc, np.where(qi == 2, -sn, -pc)))
+
+
+def synth_tracks(n_tracks: int, n_samples: int, sr: float, first_track: int = 0, first_sample: int = 0, seed: int = 0x5EED) -> np.ndarray:
+    """float32 [n_tracks, n_samples]: samples first_sample .. of tracks first_track .., as fx_synth_device_at writes them."""
+    assert first_sample % 4 == 0
+    out = np.empty((n_tracks, n_samples), np.float32)
+    quads = (n_samples + 3) // 4
+    n = first_sample + np.arange(quads * 4, dtype=np.int64)
+    isr = int(sr)
+    for i in range(n_tracks):
+        track = first_track + i
+        r = _philox4x32_10((np.uint64(first_sample // 4) + np.arange(quads, dtype=np.uint64)), seed ^ track).reshape(-1)
+        u = (r >> np.uint32(8)).astype(np.float64) * (1.0 / 8388608.0) - 1.0
+        reg = track & 7
+        sigma = 0.5 if reg == 6 else (0.001 if reg == 7 else 0.05)
+        freq = 110.0 * 2.0 ** ((track % 48) / 12.0)
+        ph = float(track) * 0.61803398874989484820
+        ph = ph - np.floor(ph)
+        turns = (freq * n.astype(np.float64)) / sr + ph
+        turns = turns - np.floor(turns)
+        x = 0.5 * _synth_sin_turns(turns) + sigma * u
+        x = np.where((n % isr) < isr // 20, x * 4.0, x)
+        if track & 1:
+            m = n % (2 * isr)
+            x = np.where((m >= isr) & (m < isr + isr // 4), 0.0, x)
+        out[i] = x[:n_samples].astype(np.float32)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 TOL = 1e-4          # BASELINE.json north_star: <= 1e-4 on normalised [0, 1] outputs
 MARGIN_TOL = 1e-4   # decisions whose relative margin is below this are exempt (and counted)
 
