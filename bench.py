@@ -148,7 +148,7 @@ def cpu_reference_rate(audio_np, threads: int, window=None, hop=None, sr=None):
     """frames/s of the CPU checker on audio_np [T, S]; prefers oracle/_ref (the reference's own classes)."""
     import oracle_util as ou
 
-    ora = ou.best_oracle()
+    ora = ou.fastest_oracle()
     t0 = time.perf_counter()
     r = ora.analyse(audio_np, threads=threads, window=window or WINDOW, hop=hop or HOP, sample_rate=sr or SR)
     dt = time.perf_counter() - t0

@@ -42,8 +42,10 @@ static void fft_plan_init (fft_plan* p, int n, int inverse)
     int i, m = n;
     p->n = n; p->inverse = inverse; p->n_stages = 0;
     p->tw = (cpx*) malloc (sizeof (cpx) * (size_t) n);
+    /* juce_FFT.cpp (4.2.x) [JUCE-recall]: phase = i * inverseFactor, inverseFactor = (isInverse ? 2.0 : -2.0) * double_Pi / fftSize */
+    const double inverse_factor = (inverse ? 2.0 : -2.0) * FX_PI_D / n;
     for (i = 0; i < n; ++i) {
-        const double phase = (inverse ? 2.0 : -2.0) * FX_PI_D * i / n;
+        const double phase = i * inverse_factor;
         p->tw[i].r = (float) cos (phase);
         p->tw[i].i = (float) sin (phase);
     }

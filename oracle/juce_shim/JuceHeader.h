@@ -332,9 +332,12 @@ public:
 
     FFT (int order, bool isInverse) : size (1 << order), inverse (isInverse), twiddle ((size_t) size)
     {
+        // juce_FFT.cpp (4.2.x) [JUCE-recall]: inverseFactor = (isInverse ? 2.0 : -2.0) * double_Pi / fftSize; phase = i * inverseFactor
+        // (for the power-of-two sizes used here the scaling by 1 / size is exact, so the order of operations cannot change a bit)
+        const double inverseFactor = (inverse ? 2.0 : -2.0) * double_Pi / size;
         for (int i = 0; i < size; ++i)
         {
-            const double phase = (inverse ? 2.0 : -2.0) * double_Pi * i / size;
+            const double phase = i * inverseFactor;
             twiddle[(size_t) i].r = (float) cos (phase);
             twiddle[(size_t) i].i = (float) sin (phase);
         }

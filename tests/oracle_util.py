@@ -137,7 +137,33 @@ def reference() -> Oracle | None:
     return Oracle(REF_SO) if os.path.exists(REF_SO) else None
 
 
-def best_oracle() -> Oracle:
+class CheckedOracle:
+    """The checker the parity tests use: VALUES from the reference's own classes (oracle/_ref), decision MARGINS from the
+    plain-C port (bit-exact with _ref on every value, and the only one of the two that reports margins).  The exemptions of
+    compare() therefore never rest on what the GPU says about its own decisions (VERDICT r1 weak #1)."""
+
+    def __init__(self):
+        self.ref = reference()
+        self.port = port()
+        self.kind = (self.ref.kind + " values + port margins") if self.ref is not None else (self.port.kind + " (oracle/_ref not built)")
+
+    def analyse(self, audio: np.ndarray, threads: int = 0, **cfg):
+        p = self.port.analyse(audio, threads=threads, **cfg)
+        if self.ref is None:
+            return p
+        r = self.ref.analyse(audio, threads=threads, **cfg)
+        # the port restates the reference bit for bit (tests/test_oracle.py): anything else is a broken checker, not a margin case
+        assert np.array_equal(r["raw"], p["raw"], equal_nan=True), "port and oracle/_ref disagree"
+        assert np.array_equal(r["diag"][..., D["lag"]], p["diag"][..., D["lag"]])
+        return {"raw": r["raw"], "smooth": r["smooth"], "diag": p["diag"], "frames": r["frames"]}
+
+
+def best_oracle() -> CheckedOracle:
+    return CheckedOracle()
+
+
+def fastest_oracle() -> Oracle:
+    """values only (timing legs of bench.py: the reference build when present)"""
     return reference() or port()
 
 
@@ -246,45 +272,63 @@ def close(a: np.ndarray, b: np.ndarray, tol: float = TOL) -> np.ndarray:
     return ok | both_nan | both_inf
 
 
+CAUSES = ("gate", "pitch", "peak", "flat", "onset")
+
+
 def compare(gpu: dict, ora: dict, tol: float = TOL, margin_tol: float = MARGIN_TOL, smooth_halo: int = 10) -> dict:
     """Compare GPU and oracle feature blocks frame by frame.
 
-    A raw mismatch is EXEMPT when a decision that feeds the value had a relative margin below margin_tol on
-    either side (pitch lag -> f0/her/oer/inharm; peak set -> inharm; flatness gate; silence gates -> everything;
-    onset comparisons).  Smoothed values are exempt for smooth_halo frames after an exempt raw frame.
-    Returns counts; 'bad_raw' / 'bad_smooth' must be zero for parity.
+    A raw mismatch is EXEMPT only when a decision that feeds the value had a relative margin below margin_tol ON THE
+    ORACLE'S SIDE (the port's margins: pitch lag -> f0/her/oer/inharm; peak set -> inharm; flatness gate; silence gates ->
+    everything; onset comparisons).  The GPU's own margins are a diagnostic: 'gpu_only_low_margin_frames' counts frames
+    the GPU flags and the oracle does not -- they exempt nothing.  An oracle without margins (-1: oracle/_ref alone, golden
+    fixtures) exempts nothing either.  Smoothed values are exempt for smooth_halo frames after a mismatching raw frame.
+    Returns counts; 'bad_raw' / 'bad_lag' / 'bad_smooth' must be zero for parity.
     """
     graw, oraw = gpu["raw"], ora["raw"]
     gd, od = gpu["diag"], ora["diag"]
 
-    def m(name):   # smallest margin seen on either side (oracle/_ref reports -1 for margins it cannot observe)
-        g = gd[..., D[name]]
+    def m(name):   # the oracle's margin
         o = od[..., D[name]]
-        o = np.where(o < 0, np.inf, o)
-        return np.minimum(g, o)
+        return np.where(o < 0, np.inf, o)
 
-    low_pitch = m("pitch_margin") < margin_tol
-    low_peak = m("peak_margin") < margin_tol
-    low_flat = m("flat_margin") < margin_tol
-    low_gate = m("gate_margin") < margin_tol
-    low_onset = m("onset_margin") < margin_tol
+    low = {"pitch": m("pitch_margin") < margin_tol, "peak": m("peak_margin") < margin_tol, "flat": m("flat_margin") < margin_tol,
+           "gate": m("gate_margin") < margin_tol, "onset": m("onset_margin") < margin_tol}
+    glow = np.zeros(low["gate"].shape, bool)
+    for name in ("pitch_margin", "peak_margin", "flat_margin", "gate_margin", "onset_margin"):
+        glow |= gd[..., D[name]] < margin_tol
+    any_low = low["pitch"] | low["peak"] | low["flat"] | low["gate"] | low["onset"]
 
     ok = close(graw, oraw, tol)
-    exempt = np.zeros_like(ok)
+    cause = {c: np.zeros_like(ok) for c in CAUSES}
     for name in ("f0", "her", "oer", "inharm"):
-        exempt[..., F[name]] |= low_pitch
-    exempt[..., F["inharm"]] |= low_peak
-    exempt[..., F["flatness"]] |= low_flat
-    exempt |= low_gate[..., None]
-    # a flipped gate on the previous non-silent decision changes which spectrum flux is measured against
-    exempt[..., F["flux"]] |= low_gate
-    exempt[..., F["onset"]] |= low_onset
+        cause["pitch"][..., F[name]] |= low["pitch"]
+    cause["peak"][..., F["inharm"]] |= low["peak"]
+    cause["flat"][..., F["flatness"]] |= low["flat"]
+    # a flipped silence gate changes everything, including which spectrum the next flux is measured against
+    cause["gate"] |= low["gate"][..., None]
+    cause["onset"][..., F["onset"]] |= low["onset"]
+    exempt = np.zeros_like(ok)
+    for c in CAUSES:
+        exempt |= cause[c]
     bad_raw = ~ok & ~exempt
 
     # lag must match exactly unless exempt
     lag_mismatch = (gd[..., D["lag"]] != od[..., D["lag"]])
-    bad_lag = lag_mismatch & ~low_pitch & ~low_gate
+    bad_lag = lag_mismatch & ~low["pitch"] & ~low["gate"]
 
+    by_cause, left = {}, ~ok & exempt
+    for c in CAUSES:                       # each exempted value is attributed to the first cause that covers it
+        hit = left & cause[c]
+        by_cause[c] = int(hit.sum())
+        left &= ~hit
+
+    # error statistics over the values that are compared numerically (finite on both sides, not exempt)
+    fin = np.isfinite(graw) & np.isfinite(oraw) & ~exempt
+    with np.errstate(invalid="ignore"):
+        abs_err = np.where(fin, np.abs(graw.astype(np.float64) - oraw.astype(np.float64)), 0.0)
+        rel_err = abs_err / np.maximum(1.0, np.abs(np.where(fin, oraw, 0.0).astype(np.float64)))
+    names = list(F)
     res = {
         "frames": int(ok.shape[0] * ok.shape[1]),
         "raw_mismatch_total": int((~ok).sum()),
@@ -292,13 +336,17 @@ def compare(gpu: dict, ora: dict, tol: float = TOL, margin_tol: float = MARGIN_T
         "bad_raw": int(bad_raw.sum()),
         "lag_mismatch": int(lag_mismatch.sum()),
         "bad_lag": int(bad_lag.sum()),
-        "low_margin_frames": int((low_pitch | low_peak | low_flat | low_gate | low_onset).sum()),
+        "low_margin_frames": int(any_low.sum()),
+        "gpu_only_low_margin_frames": int((glow & ~any_low).sum()),
+        "exempt_by_cause": by_cause,
+        "max_abs_err": {n: float(abs_err[..., F[n]].max()) if abs_err.size else 0.0 for n in names},
+        "max_rel_err": {n: float(rel_err[..., F[n]].max()) if rel_err.size else 0.0 for n in names},
     }
     if gpu.get("smooth") is not None and ora.get("smooth") is not None:
         oks = close(gpu["smooth"], ora["smooth"], tol)
         # any raw mismatch (exempt or not) contaminates the next smooth_halo frames of that feature; onset feeds on RMS
         dirty = ~ok
-        dirty[..., F["onset"]] |= low_onset
+        dirty[..., F["onset"]] |= low["onset"]
         halo = np.zeros_like(dirty)
         for k in range(min(smooth_halo + 6, dirty.shape[1])):
             halo[:, k:, :] |= dirty[:, : dirty.shape[1] - k, :] if k else dirty
@@ -306,3 +354,8 @@ def compare(gpu: dict, ora: dict, tol: float = TOL, margin_tol: float = MARGIN_T
         res["smooth_mismatch_total"] = int((~oks).sum())
         res["bad_smooth"] = int(bad_s.sum())
     return res
+
+
+def summary(res: dict) -> dict:
+    """the counts of a compare() result without the per-feature tables (one line in a log)"""
+    return {k: v for k, v in res.items() if k not in ("max_abs_err", "max_rel_err")}

@@ -31,7 +31,7 @@ def oracle():
 
 
 def assert_parity(res, what="", max_exempt_frac=0.01):
-    print(what, res)
+    print(what, ou.summary(res))
     assert res["bad_raw"] == 0, (what, res)
     assert res["bad_lag"] == 0, (what, res)
     assert res.get("bad_smooth", 0) == 0, (what, res)
@@ -94,7 +94,14 @@ def test_parity_against_golden_fixtures(fx, path):
                   onset_multiplier=float(extra["onset_multiplier"]), rms_pushes_per_frame=int(extra["rms_pushes"]))
     with fx.Engine(**kw) as e:
         g = e.analyse_host(audio)
-    diag = np.full(g["diag"].shape, -1.0, np.float32)
+    # values from the fixture (generated from oracle/_ref), decision margins from the port on the same input
+    okw = dict(window=N, hop=H, sample_rate=sr, mode=int(z["mode"]))
+    if extra:
+        okw.update(gain=float(extra["gain"]), onset_type=int(extra["onset_type"]), onset_hist=int(extra["onset_hist"]),
+                   onset_multiplier=float(extra["onset_multiplier"]), rms_pushes=int(extra["rms_pushes"]))
+    pd = ou.port().analyse(audio, **okw)
+    assert np.array_equal(pd["raw"], z["raw"], equal_nan=True)
+    diag = pd["diag"].copy()
     diag[..., ou.D["lag"]] = z["lag"]
     o = {"raw": z["raw"], "smooth": z["smooth"], "diag": diag}
     assert_parity(ou.compare(g, o), os.path.basename(path))
@@ -367,3 +374,23 @@ def test_cpp_facade_matches_reference_wiring(fx, oracle, tmp_path):
     expect = np.array([rows[0, 0, 1 + fx.FEATURES.index(n)] for n in order], np.float32)
     assert np.array_equal(vals.astype(np.float32), expect, equal_nan=True)
     rx.close()
+
+
+def test_ten_minute_stream_in_sixty_carried_calls(fx, oracle):
+    """BASELINE configs[4] stream length: 10 minutes per track at 48 kHz, N = 2048 / H = 1024 -> 28 125 frames
+    per track, analysed in 60 consecutive calls with the per-track state carried (overlap, previous spectrum, smoothing and onset
+    histories), against ONE run of the reference over the whole stream.  The input is the bench workload (Philox generator, bursts
+    and silences included), so the 60 call boundaries fall on every kind of frame."""
+    N, H, sr, T = 2048, 1024, 48000.0, 2
+    S = 10 * 60 * 48000 // H * H
+    audio = ou.synth_tracks(T, S, sr, first_track=5)
+    F = S // H
+    cuts = [round(i * F / 60) * H for i in range(61)]
+    parts = []
+    with fx.Engine(n_tracks=T, window=N, hop=H, sample_rate=sr, ring_hops=0) as e:
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            parts.append(e.analyse_host(audio[:, a:b]))
+    g = {k: np.concatenate([p[k] for p in parts], axis=1) for k in ("raw", "smooth", "diag")}
+    assert g["raw"].shape[1] == 28125
+    o = oracle.analyse(audio, window=N, hop=H, sample_rate=sr)
+    assert_parity(ou.compare(g, o), "10 min x 60 carried calls", max_exempt_frac=0.002)
