@@ -26,6 +26,19 @@
 #include "fx_kernels.cuh"
 #include <math.h>
 
+// 1: the spectral features take ONE pass over a thread's bins.  Spread, slope and energy variance are moments about values
+//    (centroid, mean energy, largest magnitude) that are only known after a block reduction; expanded, they are combinations
+//    of raw moments that the first pass can accumulate:  with x = (bin + 1/2) / M, S0 = sum mag, W1 = sum x mag,
+//    S2 = sum x^2 mag, S4 = sum mag^2
+//        sum (x - c)^2 mag        = S2 - 2 c W1 + c^2 S0                       (SpectralCharacteristics.h:135-139)
+//        sum bin * mag / maxE     = (M W1 - S0 / 2) / maxE                     (:175)
+//        sum (mag / maxE - mean)^2 = S4 / maxE^2 - M mean^2                    (:182-190)
+//    in fp64 (the cancellation costs a few of its 16 digits on features compared at 1e-4).  K1b forms them.
+// 0: the second pass over the bins (kept for A/B measurements).
+#ifndef FX_SINGLE_PASS
+#define FX_SINGLE_PASS 1
+#endif
+
 namespace fx {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -250,7 +263,9 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
     fft_stage3<R1, false> (t, sm.ex);
 }
 
-template <int R1>
+// MG: also compute the decision margins (diagnostics, FX_DIAG_*_MARGIN).  They feed nothing: a call that does not ask for the
+// diagnostics runs the instantiation without them -- same features, bit for bit (tests/test_gpu_parity.py).
+template <int R1, bool MG>
 __global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 3 : (R1 == 8 ? 6 : 12)))
 k_analyse (const AnalyseParams p)
 {
@@ -276,8 +291,10 @@ k_analyse (const AnalyseParams p)
     }
 
     const int H = p.hop, NB = N >> p.log2_hop;
+#if ! FX_SINGLE_PASS
     const double nyquist = p.sample_rate / 2.0;
     const double frpb = nyquist / (double) M;
+#endif
     const float gain = p.gain[track];
     const float* src = p.audio + track * p.track_stride;
     const float* tail = p.tail_in + track * (long) (N - H);
@@ -478,12 +495,16 @@ k_analyse (const AnalyseParams p)
         {
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0;
+#if FX_SINGLE_PASS
+            double s2 = 0.0, s4 = 0.0;
+            const double x0 = ((double) b0 + 0.5) * inv_m;                                        // (bin + 1/2) / M, exact
+#endif
             int count = 0;
             float maxre = 0.0f;
             // gate margin: the smallest distance of |Re| from sqrt (eps), relative to sqrt (eps) -- a lower bound of the
             // relative gap between Re^2 and eps ((1 + d)^2 - 1 >= d and 1 - (1 - d)^2 >= d), two instructions per bin
             const float eps_f = (float) eps;
-            const float gate_s = __fsqrt_rn (eps_f);
+            const float gate_s = MG ? __fsqrt_rn (eps_f) : 0.0f;
             const float gate_inv = gate_s > 0.0f ? __fdividef (1.0f, gate_s) : 3.0e38f;
             float gate_d = 3.0e38f;
             double mprod = 1.0; int esum = 0;
@@ -506,20 +527,35 @@ k_analyse (const AnalyseParams p)
                     mprod *= q.m;                                                                // >= 2^-8: no renormalisation needed
                     esum += q.e;
                 }
-                gate_d = fminf (gate_d, fabsf (fabsf (cr[j]) - gate_s));
+                if (MG) gate_d = fminf (gate_d, fabsf (fabsf (cr[j]) - gate_s));
+#if FX_SINGLE_PASS
+                const double x = x0 + (double) j * inv_m;                                        // fc / nyquist (:70, :137)
+                const double xm = x * mg;
+                weighted += xm;
+                s2 = fma (x, xm, s2);
+                s4 = fma (mg, mg, s4);
+#else
                 const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
                 weighted += fc * mg;
+#endif
                 maxre = fmaxf (maxre, fabsf (cr[j]));
             }
             lprod = me_from (mprod); lprod.e += esum;
+#if FX_SINGLE_PASS
+            double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, 0.0 };
+            warp_sum_t<8> (s8, lane);
+            (void) flat_sum_thread;
+#else
             double s4[4] = { mag_sum, weighted, flux, lhr };
             warp_sum_t<4> (s4, lane);
             flat_sum_thread = flat_sum;                                                           // summed with the pass-2 values
+#endif
             const int wcount = warp_addi (count);
             const float wmax = warp_max_nonneg (maxre);
             const float wraw = warp_max_nonneg (rawmax);
             const float wps = warp_sumf (psum);
-            const float wmar = warp_min_nonneg (fminf (gate_d * gate_inv, 0.5f));
+            float wmar = 1.0f;
+            if (MG) wmar = warp_min_nonneg (fminf (gate_d * gate_inv, 0.5f));
             // inclusive warp scan of the extended-range product, in bin order
             ME inc = lprod;
             #pragma unroll
@@ -532,12 +568,16 @@ k_analyse (const AnalyseParams p)
             if (lane == 0) exc = me_one();
             lprod = exc;                                                                         // lane-exclusive prefix within the warp
             if (lane == 31) { sm.scan_m[warp] = inc.m; sm.scan_e[warp] = inc.e; }
+#if FX_SINGLE_PASS
+            if (lane < 8) sm.red[1][warp_sum_slot<8> (lane)][warp] = s8[0];                      // slots 0..6: S0, W1, flux, lhr, S2, S4, flat_sum
+#else
             if (lane < 4) sm.red[1][warp_sum_slot<4> (lane)][warp] = s4[0];
+#endif
             if (lane == 0)
             {
                 sm.icount[warp] = wcount;
                 sm.fmaxs[warp] = wmax;
-                sm.fmins[0][warp] = wmar;
+                if (MG) sm.fmins[0][warp] = wmar;
                 sm.fmins[1][warp] = wraw;
                 sm.psums[warp] = wps;
             }
@@ -545,9 +585,22 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
         // every thread needs the magnitude sum, the centroid and the maxima; flux, the low-energy sum, the flatness sums
         // and the gate margin only go into the record and are combined by thread 0 when it writes it
-        double mag_sum = 0.0, weighted = 0.0;
-        float rawmax_all = 0.0f, maxre_all = 0.0f, psum_all = 0.0f;
+        double mag_sum = 0.0;
+        float maxre_all = 0.0f, psum_all = 0.0f;
         ME prefix = me_one();
+#if FX_SINGLE_PASS
+        // every thread needs the magnitude sum (silence gate), the largest |Re| (exponent budget below) and the norm of P;
+        // everything else of the pass only goes into the record and is combined by the record stage
+        #pragma unroll
+        for (int w = 0; w < NW; ++w)
+        {
+            mag_sum += sm.red[1][0][w];
+            maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
+            psum_all += sm.psums[w];
+        }
+#else
+        double weighted = 0.0;
+        float rawmax_all = 0.0f;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
@@ -556,14 +609,17 @@ k_analyse (const AnalyseParams p)
             rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
             psum_all += sm.psums[w];
         }
+#endif
         #pragma unroll 1
         for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
         const double maxmag = (double) maxre_all * (double) maxre_all;
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
+#if ! FX_SINGLE_PASS
         const float centroid = (float) (weighted / mag_sum);                                      // :127
         const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
         const double inv_max_e = 1.0 / max_e;
+#endif
         // how far 8 gated bins can move the exponent of the running flatness product: every gated magnitude lies in
         // (eps, maxmag], so its exponent is bounded by the larger of the two ends' (CTA-uniform, no per-bin bookkeeping)
         int e_budget = 0;
@@ -578,8 +634,11 @@ k_analyse (const AnalyseParams p)
         // :177 meanE = (sum of mag / maxE) / M.  The reference's third pass (:182-190, deviations from meanE) runs inside
         // this one because the mean follows from pass 1's magnitude sum: sum (mag * (1 / maxE)) and magSum * (1 / maxE)
         // differ by fp64 rounding only (1e-16 relative on a feature compared at 1e-4).
+#if ! FX_SINGLE_PASS
         const double mean_e = (mag_sum * inv_max_e) * inv_m;
+#endif
         {
+#if ! FX_SINGLE_PASS
             double var = 0.0, sie = 0.0, evar = 0.0;
             const double cn = (double) centroid / nyquist;                                        // :137
             #pragma unroll
@@ -594,6 +653,7 @@ k_analyse (const AnalyseParams p)
                 const double de = e - mean_e;                                                     // :182-190
                 evar += de * de;
             }
+#endif
             // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is still in
             // range and the exponent budget of its bins reaches a limit.  Such a thread runs the reference's own sequential IEEE
             // multiply (:92) over its 8 bins, from registers, starting at its prefix (which equals the reference's running
@@ -620,18 +680,24 @@ k_analyse (const AnalyseParams p)
                 }
                 if (left) { ev_code = (unsigned) t; ev_prod = prod; }
             }
+#if ! FX_SINGLE_PASS
             double s4[4] = { var, sie, flat_sum_thread, evar };
             warp_sum_t<4> (s4, lane);
-            const unsigned wev = warp_minu (ev_code);
             if (lane < 4) sm.red[0][1 + warp_sum_slot<4> (lane)][warp] = s4[0];                   // slots 1..4: var, sie, flat_sum, evar
+#endif
+            const unsigned wev = warp_minu (ev_code);
             if (lane == 0) sm.ucodes[0][warp] = wev;
             if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // the warp's earliest event thread
         }
         if (t == 0)
         {
             // the part of the spectral record every thread already holds (the reductions follow after the next transform)
+#if FX_SINGLE_PASS
+            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->have_prev = have_prev ? 1.0f : 0.0f;
+#else
             rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->mean_e = mean_e; rec->max_e = max_e;
             rec->centroid = centroid; rec->have_prev = have_prev ? 1.0f : 0.0f;
+#endif
         }
         if (! silent)
         {
@@ -714,7 +780,7 @@ k_analyse (const AnalyseParams p)
         // =========================== pitch: cumulative normalised difference + lag search ==============
         // workf holds d[s] (kept for the margins), workg receives cnd[s]; each thread owns s = 16 t .. 16 t + 15
         float av[16];                                                                             // ac[s] = d^2 s (PitchAnalyser.h:122-123)
-        float dv[16];
+        float dv[MG ? 16 : 1];                                                                    // d[s]: only the margins look at it again
         double seg_exc;
         {
             const float s0f = (float) (16 * t);
@@ -723,7 +789,7 @@ k_analyse (const AnalyseParams p)
             for (int j = 0; j < 16; ++j)
             {
                 const float d = sm.ex[zl_own + zrun<R1> (j)].y + sm.ex[j == 0 ? zl_self : zl_mirror + zrun<R1> (16 - j)].y;     // Z[s] + Z[N - s]: 2 * 2^k * D[s]
-                dv[j] = d;
+                if (MG) dv[j] = d;
                 av[j] = __fmul_rn (__fmul_rn (d, d), s0f + (float) j);                            // s = 0 contributes 0
                 runf += av[j];
             }
@@ -745,7 +811,7 @@ k_analyse (const AnalyseParams p)
             seg_exc = __shfl_up_sync (0xffffffffu, inc, 1);
             if (lane == 0) seg_exc = 0.0;
             if (lane == 31) sm.pscan[warp] = inc;
-            if (t == 0) sm.d0 = dv[0];
+            if (MG && t == 0) sm.d0 = dv[0];
         }
         __syncthreads();
         unsigned first_cross = 0xffffffffu, nd_mask = 0u;
@@ -765,7 +831,7 @@ k_analyse (const AnalyseParams p)
                 float c = (sumf != 0.0f) ? __fmul_rn (av[j], rcp_approx (sumf)) : 0.0f;          // :146-154
                 if (j == 0 && t == 0) c = 1.0f;                                                   // :141
                 workg[17 * t + j] = c;
-                workf[17 * t + j] = dv[j];                                                        // every read of Z is behind the barrier above
+                if (MG) workf[17 * t + j] = dv[j];                                                // every read of Z is behind the barrier above
                 if (j > 0 && ! (c < c_before)) nd_mask |= 1u << (j - 1);          // the descent (:178) stops at j - 1
                 c_before = c;
                 if (j >= 2 || t != 0)                                                             // the search starts at s = 2 (:169)
@@ -814,7 +880,7 @@ k_analyse (const AnalyseParams p)
         }
         const double hmax = (double) hmaxre * (double) hmaxre;
         const bool crossed = (s0 != 0xffffffffu);
-        const float e_abs = 1.0e-6f * fabsf (sm.d0);
+        const float e_abs = MG ? 1.0e-6f * fabsf (sm.d0) : 0.0f;
         int lag_i;                                                   // integer lag, -1 when the search found nothing (:165,188)
         float pm = 1.0f;
         if (crossed)
@@ -838,22 +904,25 @@ k_analyse (const AnalyseParams p)
             lag_i = (c_end <= c_right) ? s_end : right;
             // margins (diagnostics), spread over the whole CTA: the threshold tests s = 2 .. s0 (:176) ...
             // (work is dealt from the last warp backwards: the low lags meet the warp that has no peaks to process below)
-            const int tr = (t + 32) & (T - 1);
-            #pragma unroll 1
-            for (int s = 2 + tr; s <= (int) s0; s += T)
+            if (MG)
             {
-                const float c = workg[phys (s)];
-                pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[phys (s)], e_abs), 0.01f, 0.0f));
-            }
-            // ... and every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1
-            const int s_hi = min (s_end + 1, N - 1);
-            #pragma unroll 1
-            for (int s = (int) s0 + 1 + tr; s <= s_hi; s += T)
-            {
-                const float c = workg[phys (s)], cp = workg[phys (s - 1)];
-                const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
-                const float up = cnd_uncertainty (cp, workf[phys (s - 1)], e_abs);
-                pm = fminf (pm, noisy_margin (c, u, cp, up));
+                const int tr = (t + 32) & (T - 1);
+                #pragma unroll 1
+                for (int s = 2 + tr; s <= (int) s0; s += T)
+                {
+                    const float c = workg[phys (s)];
+                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[phys (s)], e_abs), 0.01f, 0.0f));
+                }
+                // ... and every comparison the descent made, (s - 1, s) for s = s0 + 1 .. s_end + 1
+                const int s_hi = min (s_end + 1, N - 1);
+                #pragma unroll 1
+                for (int s = (int) s0 + 1 + tr; s <= s_hi; s += T)
+                {
+                    const float c = workg[phys (s)], cp = workg[phys (s - 1)];
+                    const float u = cnd_uncertainty (c, workf[phys (s)], e_abs);
+                    const float up = cnd_uncertainty (cp, workf[phys (s - 1)], e_abs);
+                    pm = fminf (pm, noisy_margin (c, u, cp, up));
+                }
             }
         }
         else
@@ -872,17 +941,21 @@ k_analyse (const AnalyseParams p)
             for (int w = 0; w < NW; ++w) gidx = min (gidx, sm.ugidx[w]);
             lag_i = (gidx == 0xffffffffu) ? -1 : (int) gidx;
             // no crossing: every threshold test was false; runner-up of the global minimum for its margin
-            float second = 100.0f;
-            #pragma unroll 2
-            for (int j = (t == 0 ? 2 : 0); j < 16; ++j)
+            if (MG)
             {
-                const float c = workg[17 * t + j];
-                pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
-                if (16 * t + j != (int) gidx) second = fminf (second, c);
+                float second = 100.0f;
+                #pragma unroll 2
+                for (int j = (t == 0 ? 2 : 0); j < 16; ++j)
+                {
+                    const float c = workg[17 * t + j];
+                    pm = fminf (pm, noisy_margin (c, cnd_uncertainty (c, workf[17 * t + j], e_abs), 0.01f, 0.0f));
+                    if (16 * t + j != (int) gidx) second = fminf (second, c);
+                }
+                const float wsec = warp_min_nonneg (second);
+                if (lane == 0) sm.pmins[1][warp] = wsec;
             }
-            const float wsec = warp_min_nonneg (second);
-            if (lane == 0) sm.pmins[1][warp] = wsec;
         }
+        if (MG)
         {
             const float wpm = warp_min_nonneg (pm);
             if (lane == 0) sm.pmins[0][warp] = wpm;
@@ -907,26 +980,28 @@ k_analyse (const AnalyseParams p)
             double inharm = 0.0;                // sum of f0Proportion * binMagnitude; the record stage divides by the magnitude sum (:237)
             unsigned pgap = 0xffffffffu, peak_mask = 0u;
             const float mean_f = (float) mean_mag;
-            // neighbours bin-2, bin-1, bin+1 (:136-143, loop end exclusive)
-            double mgs[11];
+            // neighbours bin-2, bin-1, bin+1 (:136-143, loop end exclusive).  The magnitudes are exact squares of fp32 values in
+            // fp64, so "a neighbour's magnitude is larger" is decided by |Re| alone; only the test against the mean needs the square.
+            float aa[11];
             #pragma unroll
-            for (int j = 0; j < 11; ++j) mgs[j] = (double) ar[j] * (double) ar[j];
+            for (int j = 0; j < 11; ++j) aa[j] = fabsf (ar[j]);
             #pragma unroll
             for (int j = 0; j < 8; ++j)
             {
                 const int bin = b0 + j;
-                const double mg = mgs[2 + j];
+                const double mg = (double) ar[2 + j] * (double) ar[2 + j];
                 const float mgf = (float) mg;
-                pgap = min (pgap, ulp_gap (mgf, mean_f));
+                if (MG) pgap = min (pgap, ulp_gap (mgf, mean_f));
                 if (mg > mean_mag)
                 {
                     // edge clamps (:136-137): the neighbour window is [max (bin-2, 0), min (bin+2, M-1))
                     const int lo = bin - 2 > 0 ? bin - 2 : 0;
                     const int hi = bin + 2 < M - 1 ? bin + 2 : M - 1;                             // exclusive
+                    const float a = aa[2 + j];
                     bool peak = true;
-                    if (bin - 2 >= lo && bin - 2 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j], mgf)); if (mgs[j] > mg) peak = false; }
-                    if (peak && bin - 1 >= lo && bin - 1 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j + 1], mgf)); if (mgs[j + 1] > mg) peak = false; }
-                    if (peak && bin + 1 < hi) { pgap = min (pgap, ulp_gap ((float) mgs[j + 3], mgf)); if (mgs[j + 3] > mg) peak = false; }
+                    if (bin - 2 >= lo && bin - 2 < hi) { if (MG) pgap = min (pgap, ulp_gap (__fmul_rn (aa[j], aa[j]), mgf)); if (aa[j] > a) peak = false; }
+                    if (peak && bin - 1 >= lo && bin - 1 < hi) { if (MG) pgap = min (pgap, ulp_gap (__fmul_rn (aa[j + 1], aa[j + 1]), mgf)); if (aa[j + 1] > a) peak = false; }
+                    if (peak && bin + 1 < hi) { if (MG) pgap = min (pgap, ulp_gap (__fmul_rn (aa[j + 3], aa[j + 3]), mgf)); if (aa[j + 3] > a) peak = false; }
                     if (peak) peak_mask |= 1u << j;
                 }
             }
@@ -991,9 +1066,9 @@ k_analyse (const AnalyseParams p)
             double s1[1] = { inharm };
             warp_sum<1> (s1);
             const int wnp = warp_addi (npeaks);
-            const float wpk = warp_min_nonneg (pkm);
             if (lane == 0) sm.red[1][7][warp] = s1[0];                                            // slot 7: inharmonicity sum
-            if (lane == 0) { sm.ipeaks[warp] = wnp; sm.fmins[2][warp] = wpk; }
+            if (lane == 0) sm.ipeaks[warp] = wnp;
+            if (MG) { const float wpk = warp_min_nonneg (pkm); if (lane == 0) sm.fmins[2][warp] = wpk; }
         }
         __syncthreads();
         // ---- the frame's record (what K1b needs), one part per warp ---------------------------------------------------
@@ -1034,10 +1109,14 @@ k_analyse (const AnalyseParams p)
             {
                 const double inharm = sum_nw (ld ? sm.red[1][7][lane] : 0.0);
                 const int npeaks = warp_addi (ld ? sm.ipeaks[lane] : 0);
-                const float pkm = warp_min_nonneg (ld ? sm.fmins[2][lane] : 1.0f);
-                float pmm = warp_min_nonneg (ld ? sm.pmins[0][lane] : 1.0f);
-                const float second = warp_min_nonneg (ld ? sm.pmins[1][lane] : 100.0f);
-                if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float (gbest), second));
+                float pkm = 1.0f, pmm = 1.0f;
+                if (MG)
+                {
+                    pkm = warp_min_nonneg (ld ? sm.fmins[2][lane] : 1.0f);
+                    pmm = warp_min_nonneg (ld ? sm.pmins[0][lane] : 1.0f);
+                    const float second = warp_min_nonneg (ld ? sm.pmins[1][lane] : 100.0f);
+                    if (! crossed) pmm = fminf (pmm, relmargin_f (__uint_as_float (gbest), second));
+                }
                 if (lane == 0)
                 {
                     rec->lag = (float) lag_i; rec->pitch_margin = pmm;
@@ -1048,16 +1127,28 @@ k_analyse (const AnalyseParams p)
             if (warp == 2 % NW)
             {
                 const double flux = sum_nw (ld ? sm.red[1][2][lane] : 0.0), lhr = sum_nw (ld ? sm.red[1][3][lane] : 0.0);
-                const double flat_sum = sum_nw (ld ? sm.red[0][3][lane] : 0.0);
+                const double flat_sum = sum_nw (ld ? sm.red[FX_SINGLE_PASS ? 1 : 0][FX_SINGLE_PASS ? 6 : 3][lane] : 0.0);
                 const int count = warp_addi (ld ? sm.icount[lane] : 0);
                 if (lane == 0) { rec->flux = flux; rec->lhr = lhr; rec->flat_sum = flat_sum; rec->count = (double) count; }
             }
             if (warp == 3 % NW)
             {
+                const float flat_margin = MG ? warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f) : 1.0f;
+#if FX_SINGLE_PASS
+                // the raw moments (K1b forms spread, slope sums and energy variance from them) and the slope's largest value (:153-163)
+                const double w1 = sum_nw (ld ? sm.red[1][1][lane] : 0.0), s2 = sum_nw (ld ? sm.red[1][4][lane] : 0.0);
+                const double s4 = sum_nw (ld ? sm.red[1][5][lane] : 0.0);
+                const float rawmax_all = warp_max_nonneg (ld ? sm.fmins[1][lane] : 0.0f);
+                if (lane == 0)
+                {
+                    rec->weighted = w1; rec->var = s2; rec->evar = s4; rec->flat_margin = flat_margin;
+                    rec->max_e = fmax ((double) rawmax_all, maxmag);
+                }
+#else
                 const double var = sum_nw (ld ? sm.red[0][1][lane] : 0.0), sie = sum_nw (ld ? sm.red[0][2][lane] : 0.0);
                 const double evar = sum_nw (ld ? sm.red[0][4][lane] : 0.0);
-                const float flat_margin = warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f);
                 if (lane == 0) { rec->var = var; rec->sie = sie; rec->evar = evar; rec->flat_margin = flat_margin; }
+#endif
             }
             if (warp == 4 % NW)
             {
@@ -1144,6 +1235,22 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
     const float log_rms = (float) log10 ((double) __fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));       // RealTimeAnalyser.h:208
     const double eps = 0.01 * (double) log_rms;                                                   // :108
     const bool silent = ! (r.mag_sum > 0.05);                                                     // :121-123
+#if FX_SINGLE_PASS
+    // K1 leaves raw moments over x = (bin + 1/2) / M = fc / nyquist: weighted = W1 = sum x mag, var = S2 = sum x^2 mag,
+    // evar = S4 = sum mag^2 (see FX_SINGLE_PASS at the top of this file)
+    const double w1 = r.weighted, s2 = r.var, s4 = r.evar;
+    const float  centroid = (float) ((w1 * nyquist) / r.mag_sum);                                 // :127 weighted / magSum
+    const double cn = (double) centroid / nyquist;                                                // :137
+    const double var = (s2 - 2.0 * cn * w1) + cn * cn * r.mag_sum;                                // :135-139
+    const double inv_max_e = 1.0 / r.max_e;
+    const double mean_e = (r.mag_sum * inv_max_e) / (double) M;                                   // :177
+    const double sie = ((double) M * w1 - 0.5 * r.mag_sum) * inv_max_e;                           // :175 sum i e_i
+    double evar = s4 * inv_max_e * inv_max_e - (double) M * mean_e * mean_e;                      // :182-190
+    if (evar < 0.0) evar = 0.0;                                   // rounding of the difference (a spectrum flat to ~1e-8)
+#else
+    const float  centroid = r.centroid;
+    const double var = r.var, mean_e = r.mean_e, sie = r.sie, evar = r.evar;
+#endif
     float gate_margin = fminf (relmargin_d (r.mag_sum, 0.05), relmargin_d (r.max_e, 0.0001));
     float o_centroid = 0.0f, o_spread = 0.0f, o_flat = 0.0f, o_ler = 0.0f, o_flux = 0.0f, o_slope = 0.0f;
     if (! silent)
@@ -1152,18 +1259,18 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         const double inv = 1.0 / (r.count > 0.0 ? r.count : 1.0);                                 // :130
         const float flat = r.flat_sum > eps ? (float) (pow (r.product, inv) / (inv * r.flat_sum)) : 0.0f;     // :57-60
         o_flat = (float) log10 ((double) flat * 9.0 + 1.0);                                       // :132
-        const float c = __fdiv_rn (r.centroid, (float) (nyquist / 2.0));                          // :133
+        const float c = __fdiv_rn (centroid, (float) (nyquist / 2.0));                            // :133
         o_centroid = (float) log10 ((double) __fadd_rn (__fmul_rn (c, 9.0f), 1.0f));              // :134
-        const float max_spread = (float) (((double) r.centroid / nyquist) * (1.0 - ((double) r.centroid / nyquist)));   // :140
-        o_spread = (float) ((r.var / r.mag_sum) / (double) max_spread);                           // :141
+        const float max_spread = (float) (((double) centroid / nyquist) * (1.0 - ((double) centroid / nyquist)));   // :140
+        o_spread = (float) ((var / r.mag_sum) / (double) max_spread);                             // :141
         o_ler = (float) (r.lhr / r.mag_sum);                                                      // :125
         o_flux = r.have_prev != 0.0f ? (float) (r.flux / (double) max_flux) : 0.0f;               // :112 (K2 fixes the chunk's first non-silent frame)
     }
     if (r.max_e > 0.0001)                                                                         // :165-167
     {
-        const double energy_var = r.evar / (double) M;
+        const double energy_var = evar / (double) M;
         const double bin_std = sqrt (p.bin_var), energy_std = sqrt (energy_var);
-        const double rr = (r.sie - ((double) M * r.mean_e * 0.5)) / (double) ((float) M - 1.0f) * energy_std * bin_std;   // :195
+        const double rr = (sie - ((double) M * mean_e * 0.5)) / (double) ((float) M - 1.0f) * energy_std * bin_std;   // :195
         o_slope = (float) (rr * (bin_std / energy_std));                                          // :198
     }
 
@@ -1236,8 +1343,16 @@ template <int R1> static cudaError_t launch_t (long n_tracks, const AnalyseParam
 {
     const long grid = n_tracks * p.n_chunks;
     if (grid <= 0) return cudaSuccess;
-    k_analyse<R1><<<(unsigned) grid, 16 * R1, sizeof (Smem<R1>), stream>>> (p);
+    if (p.want_margins) k_analyse<R1, true><<<(unsigned) grid, 16 * R1, sizeof (Smem<R1>), stream>>> (p);
+    else                k_analyse<R1, false><<<(unsigned) grid, 16 * R1, sizeof (Smem<R1>), stream>>> (p);
     return cudaGetLastError();
+}
+
+template <int R1> static cudaError_t configure_t()
+{
+    cudaError_t ce = cudaFuncSetAttribute (k_analyse<R1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
+    if (ce != cudaSuccess) return ce;
+    return cudaFuncSetAttribute (k_analyse<R1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
 }
 
 size_t analyse_smem_bytes (int window)
@@ -1255,9 +1370,9 @@ cudaError_t configure_analyse (int window)
 {
     switch (window)
     {
-        case 1024: return cudaFuncSetAttribute (k_analyse<4>,  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<4>));
-        case 2048: return cudaFuncSetAttribute (k_analyse<8>,  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<8>));
-        case 4096: return cudaFuncSetAttribute (k_analyse<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<16>));
+        case 1024: return configure_t<4>();
+        case 2048: return configure_t<8>();
+        case 4096: return configure_t<16>();
         default:   return cudaErrorInvalidValue;
     }
 }

@@ -36,6 +36,7 @@ struct AnalyseParams
     int          hop;
     int          log2_hop;
     int          use_bulk;         // 1: cp.async.bulk (16-byte aligned source), 0: plain loads
+    int          want_margins;     // 1: the decision margins (diagnostics) are computed as well; 0: the instantiation without them
     const float* gain;             // [n_tracks]
     double       sample_rate;
     double       bin_var;          // slope: sum ((i/M - 0.5)^2) / M evaluated on the host in the reference's order

@@ -23,10 +23,38 @@
 
 #include <linux/futex.h>
 #include <sched.h>
+#if defined (__SSE2__) && ! defined (__SANITIZE_THREAD__)
+ #include <emmintrin.h>
+ #define FX_RING_STREAMING_STORES 1      // ThreadSanitizer does not see intrinsic stores: its build copies with memcpy
+#else
+ #define FX_RING_STREAMING_STORES 0
+#endif
 #include <sys/syscall.h>
 #include <unistd.h>
 
 namespace fx {
+
+// The ring is written once by the audio thread and read next by the GPU's copy engine: streaming (non-temporal) stores
+// skip the read-for-ownership of the destination lines and leave the audio thread's cache to the host application.  They
+// are weakly ordered, so ring_fence() goes between the copies of a push and the publishing stores.
+inline void ring_copy (float* dst, const float* src, size_t n) noexcept
+{
+#if FX_RING_STREAMING_STORES
+    if (((reinterpret_cast<uintptr_t> (dst) | reinterpret_cast<uintptr_t> (src)) & 15u) == 0 && (n & 3u) == 0)
+    {
+        for (size_t i = 0; i < n; i += 4)
+            _mm_stream_si128 (reinterpret_cast<__m128i*> (dst + i), _mm_load_si128 (reinterpret_cast<const __m128i*> (src + i)));
+        return;
+    }
+#endif
+    std::memcpy (dst, src, n * sizeof (float));
+}
+inline void ring_fence() noexcept
+{
+#if FX_RING_STREAMING_STORES
+    _mm_sfence();
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------
 class WakeWord
@@ -93,7 +121,19 @@ public:
     // some track completed a hop, so that the caller signals each group once.
     bool push (long first_track, long n, const float* const* channels, long n_samples, long hop, unsigned char* crossed) noexcept
     {
+        // (calls for more tracks than the decision bitmap holds are split: each part is all-or-nothing on its own)
+        for (long at = 0; at < n; at += kMaxPushTracks)
+            if (! push_part (first_track + at, n - at < kMaxPushTracks ? n - at : kMaxPushTracks, channels + at, n_samples, hop, crossed)) return false;
+        return true;
+    }
+
+    static constexpr long kMaxPushTracks = 16384;
+
+    bool push_part (long first_track, long n, const float* const* channels, long n_samples, long hop, unsigned char* crossed) noexcept
+    {
         Inside inside (producers_inside);              // deactivate() waits for the producers that may have seen the old flag
+        uint64_t take[kMaxPushTracks / 64];            // which tracks this call feeds: each track's flag is read exactly once
+        for (long i = 0; i < (n + 63) / 64; ++i) take[i] = 0;
         for (long i = 0; i < n; ++i)
         {
             const long t = first_track + i;
@@ -101,17 +141,25 @@ public:
             const long w = wpos[(size_t) t].load (std::memory_order_relaxed);
             const long r = rpos[(size_t) group_of (t)].load (std::memory_order_acquire);
             if (w + n_samples - r > L) return false;
+            take[i >> 6] |= 1ull << (i & 63);
         }
         for (long i = 0; i < n; ++i)
         {
+            if (! ((take[i >> 6] >> (i & 63)) & 1ull)) continue;
             const long t = first_track + i;
-            if (active[(size_t) t].load (std::memory_order_acquire) == 0u) continue;
             const long w = wpos[(size_t) t].load (std::memory_order_relaxed);
             float* ring = row (t);
             const long o = w % L;
             const long first = (o + n_samples <= L) ? n_samples : L - o;
-            std::memcpy (ring + o, channels[i], (size_t) first * sizeof (float));
-            if (first < n_samples) std::memcpy (ring, channels[i] + first, (size_t) (n_samples - first) * sizeof (float));
+            ring_copy (ring + o, channels[i], (size_t) first);
+            if (first < n_samples) ring_copy (ring, channels[i] + first, (size_t) (n_samples - first));
+        }
+        ring_fence();
+        for (long i = 0; i < n; ++i)
+        {
+            if (! ((take[i >> 6] >> (i & 63)) & 1ull)) continue;
+            const long t = first_track + i;
+            const long w = wpos[(size_t) t].load (std::memory_order_relaxed);
             wpos[(size_t) t].store (w + n_samples, std::memory_order_release);           // publish
             if (crossed != nullptr && (w / hop) != ((w + n_samples) / hop)) crossed[group_of (t)] = 1;
         }

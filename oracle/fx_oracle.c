@@ -308,6 +308,16 @@ static void spectral_characteristics (track* t, const float* buf, double rms, do
     max_flux = (M * (M + 1)) / 2.0f;                                            /* :111 */
     flux /= max_flux;
     t->diag[FXO_DIAG_FLAT_COUNT] = (float) count;
+    /* Margin of the gate decisions (diagnostic only).  The gate compares Re^2 with eps, and Re carries the absolute rounding
+     * noise of an fp32 FFT -- this transform's as much as any other implementation's -- taken as 1e-6 of the spectrum's rms
+     * (the same floor the pitch margin below discounts; an fp32 radix-4 FFT of this length is good to a few 1e-7 of the rms).
+     * For every bin the relative gap shrinks by at most 2 e / sqrt (eps) + e^2 / eps: a bin whose gap is inside that band is
+     * decided by the transform's rounding, in the reference itself too. */
+    if (eps > 0.0) {
+        const double e_abs = 1.0e-6 * sqrt (mag_sum / (double) M);
+        const double fm = (double) t->diag[FXO_DIAG_FLAT_MARGIN] - (2.0 * e_abs / sqrt (eps) + e_abs * e_abs / eps);
+        t->diag[FXO_DIAG_FLAT_MARGIN] = fm > 0.0 ? (float) fm : 0.0f;
+    }
     margin_min (&t->diag[FXO_DIAG_GATE_MARGIN], relmargin (mag_sum, 0.05));
 
     if (! (mag_sum > 0.05)) {                                                   /* :121-123: prev NOT updated */

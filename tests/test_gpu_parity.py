@@ -394,3 +394,21 @@ def test_ten_minute_stream_in_sixty_carried_calls(fx, oracle):
     assert g["raw"].shape[1] == 28125
     o = oracle.analyse(audio, window=N, hop=H, sample_rate=sr)
     assert_parity(ou.compare(g, o), "10 min x 60 carried calls", max_exempt_frac=0.002)
+
+
+@pytest.mark.parametrize("N,H,sr", [(4096, 1024, 48000.0), (2048, 1024, 48000.0), (2048, 512, 48000.0), (1024, 512, 44100.0)])
+def test_features_do_not_depend_on_the_diagnostics(fx, N, H, sr):
+    """A call that does not ask for the diagnostics runs the kernel instantiation without the decision margins (they feed
+    nothing).  Raw and smoothed features must be the same bits either way, including NaN input (the no-crossing branch of
+    the lag search) and silence."""
+    T = 12
+    audio = ou.make_tracks(T, 40 * H, sr)
+    audio[3, 7 * H + 5] = np.nan
+    audio[4] = 0.0
+    with fx.Engine(n_tracks=T, window=N, hop=H, sample_rate=sr, ring_hops=0) as e:
+        a = e.analyse_host(audio, want_diag=True)
+        e.reset()
+        b = e.analyse_host(audio, want_diag=False)
+    assert b["diag"] is None
+    assert np.array_equal(a["raw"], b["raw"], equal_nan=True)
+    assert np.array_equal(a["smooth"], b["smooth"], equal_nan=True)

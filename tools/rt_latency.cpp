@@ -81,9 +81,10 @@ int main (int argc, char** argv)
     for (auto& h : sh.hops_seen) h.store (0);
     sh.multi_hop_batches.assign ((size_t) sh.n_groups, 0);
 
-    // a few seconds of synthetic audio per track, prepared up front (the audio thread of a real host receives its blocks from
-    // the device; generating them here would be charged to the callback)
-    const long loop_blocks = std::min<long> (n_blocks, (long) (4.0 * sr / block));
+    // synthetic audio per track, prepared up front (the audio thread of a real host receives its blocks from the device;
+    // generating them here would be charged to the callback)
+    // (16 blocks per track, 8 MB in all: like a device's block buffers they stay cache resident, the content does not matter to the timing)
+    const long loop_blocks = std::min<long> (n_blocks, 16);
     const long loop_len = loop_blocks * block;
     std::vector<float> audio ((size_t) tracks * (size_t) loop_len);
     unsigned rng = 12345u;
