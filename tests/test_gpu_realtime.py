@@ -286,3 +286,67 @@ def test_osc_batch_encoder_matches_the_published_block(fx):
                 expect = np.array([vec[t, fx.FEATURES.index(n)] for n in order], np.float32)
                 assert np.array_equal(vals, expect, equal_nan=True)
         assert e.osc_encode([1], ["/x"], stride=16) == [b""]              # does not fit the stride: size 0
+
+
+def test_sixty_hz_osc_output_of_512_tracks_two_senders_each(fx, tmp_path):
+    """SURVEY.md section 8 row f1 as written: OSC at 60 Hz per track from the feature block.  512 AnalyserTrackControllers, two
+    senders each (AnalyserTrackController.h:22-23), timers started by connectToAddress (OSCFeatureAnalysisOutput.h:133); the
+    shared timer thread encodes all 1024 datagrams of a tick in one pass (fx_osc_encode_tracks) and ships them with sendmmsg.
+    Datagrams are counted on both ports and the last one of every track is compared byte for byte with the final features."""
+    import os
+    import socket
+    import subprocess
+    import threading
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    exe = tmp_path / "osc_driver"
+    lib = os.path.join(root, "feature-extractor_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(here, "cpp", "osc_driver.cpp"), "-L" + lib, "-lfxb200", "-lpthread",
+                    "-Wl,-rpath," + lib], check=True)
+    T, seconds = 512, 2.0
+    socks, got, stop = [], [[], []], threading.Event()
+    for _ in range(2):
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        s.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 64 << 20)
+        s.bind(("127.0.0.1", 0))
+        s.settimeout(0.2)
+        socks.append(s)
+
+    def rx(i):
+        while not stop.is_set():
+            try:
+                got[i].append(socks[i].recv(4096))
+            except socket.timeout:
+                pass
+
+    threads = [threading.Thread(target=rx, args=(i,)) for i in range(2)]
+    for th in threads:
+        th.start()
+    out = subprocess.run([str(exe), str(T), str(seconds), str(socks[0].getsockname()[1]), str(socks[1].getsockname()[1]), str(tmp_path / "final.f32")],
+                         capture_output=True, text=True, timeout=120)
+    time.sleep(0.5)
+    stop.set()
+    for th in threads:
+        th.join()
+    print(out.stdout, out.stderr[-500:])
+    assert out.returncode == 0, out.stderr[-500:]
+    words = out.stdout.split()
+    ticks, sent = int(words[words.index("ticks") + 1]), int(words[words.index("datagrams") + 1])
+    assert "push_errors 0" in out.stdout
+    assert ticks >= int(60 * seconds * 0.9)                              # the timer thread held 60 Hz
+    assert sent >= ticks * 2 * T * 0.98                                  # every tick carried both senders of every track
+    final = np.frombuffer((tmp_path / "final.f32").read_bytes(), np.float32).reshape(T, 12)
+    for i in range(2):
+        assert len(got[i]) >= 0.8 * ticks * T, (len(got[i]), ticks)      # (the loopback socket may drop under this burst rate)
+        last = {}
+        for g in got[i]:
+            assert g.startswith(b"/Audio/A") and len(g) in (76, 80)
+            alen = (g.index(b"\0") + 4) & ~3
+            assert g[alen:alen + 16] == b",ffffffffffff\0\0\0"
+            last[int(g[8:g.index(b"\0")])] = g[alen + 16:]
+        assert len(last) == T
+        for t in range(T):
+            vals = np.frombuffer(last[t], ">f4").astype(np.float32)
+            expect = np.array([final[t, fx.FEATURES.index(n)] for n in fx.OSC_ORDER_CODE], np.float32)
+            assert np.array_equal(vals, expect, equal_nan=True), t

@@ -6,7 +6,7 @@ Every SASS instruction is attributed to the OUTERMOST source line of its inline 
 k_analyse that the work was written on; the lines map to phases through the `// ====` section markers of fx_analyse.cu.
 fft_core is one out-of-line function called twice per frame: it is reported as its own phase, split by stage.
 
-Usage: ncu_phases.py rep.ncu-rep [n_frames] [R1]      (needs the matching lib/libfxb200.so built with -lineinfo;
+Usage: ncu_phases.py rep.ncu-rep [n_frames] [R1] [MG]    (needs the matching lib/libfxb200.so built with -lineinfo;
                                                         FXLIB selects another build)"""
 import collections, csv, io, json, os, re, subprocess, sys, tempfile
 
@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 4096 * 468
 R1 = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+MG = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # the instantiation with (1) / without (0) the decision margins
 THREADS = 16 * R1
 lib = os.environ.get("FXLIB", os.path.join(ROOT, "feature-extractor_b200/lib/libfxb200.so"))
 src_path = os.path.join(ROOT, "feature-extractor_b200/csrc/fx_analyse.cu")
@@ -37,7 +38,7 @@ marks = [
     ("filter + window + RMS", find(src, "one-pole filter + window -> work array")),
     ("FFT-alpha gather", find(src, "FFT-alpha: z = x w + i onepole")),
     ("split + spectral pass 1", find(src, "previous non-silent spectrum of this thread's bins")),
-    ("combine + spectral pass 2", find(src, "every thread needs the magnitude sum")),
+    ("combine + flatness range events", find(src, "every thread needs the magnitude sum")),
     ("FFT-beta gather", find(src, "FFT-beta: z = x + i 2^k P")),
     ("flatness prefetch + hop prefetch", find(src, "The flatness product's continuation (record stage, below) starts")),
     ("pitch (cnd scan, lag search)", find(src, "pitch: cumulative normalised difference + lag search")),
@@ -71,7 +72,7 @@ subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, "fx_analyse.sm_100a.cubin")], capture_output=True, text=True).stdout
 
 # address -> (outermost file, line, innermost file, line, in_fft_core, opcode)
-kern = f"k_analyseILi{R1}E"
+kern = f"k_analyseILi{R1}ELb{MG}E"
 a2 = {}
 infunc = in_core = False
 pending, cur = [], None                   # annotations since the last instruction: innermost first, outermost last
