@@ -258,9 +258,13 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
     const int t = threadIdx.x;
     fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1, sm.tw1f);
     __syncthreads();
+#if FX_STAGE23_SHFL
+    fft_stage23_shfl<R1, false> (t, sm.ex, sm.tw2);         // experiment: the 2 -> 3 exchange by warp shuffles (measured slower)
+#else
     fft_stage2<R1, false> (t, sm.ex, sm.tw2);
     __syncwarp();                                           // rows are private to a half warp from here on
     fft_stage3<R1, false> (t, sm.ex);
+#endif
 }
 
 // MG: also compute the decision margins (diagnostics, FX_DIAG_*_MARGIN).  They feed nothing: a call that does not ask for the

@@ -250,6 +250,55 @@ __device__ __forceinline__ void fft_stage3 (int t, float2* __restrict__ ex)
     for (int s = 0; s < 16; ++s) col[out_index<16> (s)] = v[s];
 }
 
+// EXPERIMENT (FX_STAGE23_SHFL=1, off by default): stages 2 and 3 with the 2 -> 3 exchange done by warp shuffles inside the
+// half warp instead of through shared memory -- the "warp-shuffle butterflies for the small stages" of BASELINE.json's
+// north_star.  The exchange is a 16 x 16 transpose over 16 lanes: four rounds (lane ^ 8, 4, 2, 1), each moving half of a
+// lane's 16 complex values = 64 shuffles of 32 bits per round pair... 128 SHFL + the selects that pick what to send and
+// where to put it, against 16 STS.64 + 16 LDS.64 for the shared-memory form.  Measured slower; kept
+// so that the number can be reproduced.
+#ifndef FX_STAGE23_SHFL
+#define FX_STAGE23_SHFL 0
+#endif
+template <int R1, bool INV>
+__device__ __forceinline__ void fft_stage23_shfl (int t, float2* __restrict__ ex, const float2* __restrict__ tw2)
+{
+    using D = FftDims<R1>;
+    const int k1 = t >> 4, n3 = t & 15;
+    float2* row = ex + k1 * D::ROW + n3;
+    float2 v[16], u[16];
+    #pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
+    butterfly<16, INV> (v);
+    #pragma unroll
+    for (int s = 0; s < 16; ++s)
+    {
+        const int k2 = out_index<16> (s);
+        float2 val = v[s];
+        if (k2 > 0) val = cmulw<INV> (val, tw2[(k2 - 1) * 16 + n3]);
+        u[k2] = val;                                       // natural order: lane n3 holds Y_n3[k2], k2 = 0 .. 15
+    }
+    // transpose over the 16 lanes of the half warp: element (lane L, index I) moves to (lane I, index L)
+    #pragma unroll
+    for (int b = 8; b > 0; b >>= 1)
+    {
+        const bool up = (n3 & b) != 0;
+        #pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            if (i & b) continue;
+            const float2 send = up ? u[i] : u[i | b];
+            float2 recv;
+            recv.x = __shfl_xor_sync (0xffffffffu, send.x, b);
+            recv.y = __shfl_xor_sync (0xffffffffu, send.y, b);
+            if (up) u[i] = recv; else u[i | b] = recv;
+        }
+    }
+    butterfly<16, INV> (u);                                // lane k2 now holds Y_n3[k2] at index n3
+    float2* col = ex + k1 * D::ROW + n3 * 17;              // (this lane's k2 is its index in the half warp)
+    #pragma unroll
+    for (int s = 0; s < 16; ++s) col[out_index<16> (s)] = u[s];
+}
+
 // position of spectrum bin k / of time sample n in the exchange buffer (see the header comment)
 template <int R1> __device__ __forceinline__ int zpos (int k)
 {

@@ -75,6 +75,28 @@ void fxo_fft_inverse (float* inout_2n, int n);
  * Formats: 1 U8, 2 S8, 3 S16LE, 4 S16BE, 5 S24LE, 6 S24BE, 7 S32LE, 8 S32BE, 9 F32LE, 10 F32BE.  Returns n_samples or -1. */
 long fxo_pcm_decode (const void* pcm, int format, int n_channels, int channel, long n_samples, float* out);
 
+/* ---- legacy offline analyser (AudioAnalysis.h: AudioAnalyser) ------------------------------------------------------
+ * The application never instantiates AudioAnalyser, and the block of performSpectralAnalysis that would produce features is
+ * commented out at its call site (AudioAnalysis.h:219-247); the member functions themselves are intact.  This entry point
+ * drives them the way that block does, frame by frame: the framing and windowing of performSpectralAnalysis (:134-181: frame i is
+ * centred on sample i * stepSize, zero padded at the ends, symmetric Bartlett ramps), performFrequencyOnlyForwardTransform
+ * (:208, true magnitudes), fftOut <- the first N/2 + 1 magnitudes (:226-227), calculateSpectralCharacteristics (:463-515),
+ * calculateNormalisedSpectralSlope (:566-609), calculateHarmonicCharacteristics (:253-306: histogram of peak intervals, previousF0
+ * hysteresis, inharmonicity), energyEnvelope (:249), then analyseNormalisedZeroCrosses (:517-541) and setLogAttackTime (:611-622).
+ * One channel.  out is [n_frames][FXL_NUM]; *log_attack receives estimatedLogAttackTime.  Returns n_frames or -1. */
+enum {
+    FXL_CENTROID = 0,   /* centroid / nyquist                      (:514) */
+    FXL_SPREAD, FXL_FLATNESS, FXL_FLUX,
+    FXL_SLOPE,          /* calculateNormalisedSpectralSlope         */
+    FXL_F0, FXL_HER, FXL_INHARM,
+    FXL_ZCR,            /* zero crossings * 2 / stepSize            (:538) */
+    FXL_ENERGY,         /* energy envelope: sum of the frame's magnitudes (:249) */
+    FXL_NUM_PEAKS,      /* diagnostics: number of peak bins (:361-369) */
+    FXL_NUM
+};
+long fxo_legacy_analyse (int window, double sample_rate, const float* audio, long n_samples, int n_frames,
+                         float* out, float* log_attack);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@
 #include <string>
 #include <functional>
 #include <sstream>
+#include <iostream>
 #include <algorithm>
 
 // ---------------------------------------------------------------------------------------------
@@ -115,7 +116,61 @@ public:
     Range (T s, T e) : start (s), end (e) {}
     T getStart() const { return start; }
     T getEnd()   const { return end; }
+    void setStart (T s) { start = s; if (end < s) end = s; }
+    void setEnd (T e)   { end = e; if (e < start) start = e; }
     T start, end;
+};
+
+// ---------------------------------------------------------------------------------------------
+// ReferenceCountedObject / ReferenceCountedObjectPtr / HeapBlock: only what the legacy offline analyser's headers
+// (AudioFeatures.h, AudioAnalysis.h) need to compile; the drivers never share ownership
+class ReferenceCountedObject
+{
+public:
+    void incReferenceCount() noexcept { ++refCount; }
+    void decReferenceCount() noexcept { if (--refCount == 0) delete this; }
+    int getReferenceCount() const noexcept { return refCount; }
+protected:
+    ReferenceCountedObject() : refCount (0) {}
+    virtual ~ReferenceCountedObject() {}
+private:
+    int refCount;
+};
+
+template <class T>
+class ReferenceCountedObjectPtr
+{
+public:
+    ReferenceCountedObjectPtr() : obj (nullptr) {}
+    ReferenceCountedObjectPtr (T* o) : obj (o) { if (obj) obj->incReferenceCount(); }
+    ReferenceCountedObjectPtr (const ReferenceCountedObjectPtr& o) : obj (o.obj) { if (obj) obj->incReferenceCount(); }
+    ~ReferenceCountedObjectPtr() { if (obj) obj->decReferenceCount(); }
+    ReferenceCountedObjectPtr& operator= (const ReferenceCountedObjectPtr& o)
+    {
+        if (o.obj) o.obj->incReferenceCount();
+        if (obj) obj->decReferenceCount();
+        obj = o.obj;
+        return *this;
+    }
+    T* operator->() const { return obj; }
+    T* get() const { return obj; }
+    operator T*() const { return obj; }
+private:
+    T* obj;
+};
+
+template <class T>
+class HeapBlock
+{
+public:
+    HeapBlock() {}
+    explicit HeapBlock (size_t n) : data (n) {}
+    void allocate (size_t n, bool) { data.assign (n, T()); }
+    T* getData() { return data.data(); }
+    T& operator[] (size_t i) { return data[i]; }
+    operator T*() { return data.data(); }
+private:
+    std::vector<T> data;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -197,6 +252,10 @@ public:
         }
     }
 
+    void applyGain (int startSample, int numSamples, float gain) noexcept
+    {
+        for (int ch = 0; ch < numChannels; ++ch) applyGain (ch, startSample, numSamples, gain);
+    }
     void applyGain (int channel, int startSample, int numSamples, float gain) noexcept
     {
         if (gain != 1.0f && ! isClear)

@@ -31,6 +31,9 @@
 #include "SpectralCharacteristics.h"
 #include "HarmonicCharacteristics.h"
 #include "RealTimeAnalyser.h"
+// the legacy offline analyser (never instantiated by the application; driven by fxo_legacy_analyse below)
+#include "AudioFeatures.h"
+#include "AudioAnalysis.h"
 #undef private
 
 #include "fx_oracle_api.h"
@@ -230,6 +233,64 @@ long fxo_analyse_tracks (const fxo_config* cfg, const float* audio, long n_track
     }
     for (auto& th : pool) th.join();
     return frames;
+}
+
+long fxo_legacy_analyse (int window, double sample_rate, const float* audio, long n_samples, int n_frames,
+                         float* out, float* log_attack)
+{
+    if (window < 16 || (window & (window - 1)) != 0 || n_frames < 1 || n_samples < n_frames) return -1;
+    const int N = window;
+    AudioAnalyser analyser (N, 1, sample_rate / 2.0, true, true);
+    ConcatenatedFeatureBuffer features (1, (int) n_samples, n_frames, N / 2 + 1, 1000.0 * (double) n_samples / sample_rate, sample_rate);
+    for (long i = 0; i < n_samples; ++i) features.audioOutput.setSample (0, (int) i, audio[i]);
+
+    // ---- performSpectralAnalysis (AudioAnalysis.h:121-251) with the commented-out feature block (:219-247) reinstated -------
+    const int numInputSamples = features.audioOutput.getNumSamples();
+    const int stepSize = numInputSamples / features.numDownsamples;                     // :130
+    const int numFFTInputSamples = analyser.fftIn.getNumSamples();
+    features.nyquistFrequency = features.sampleRate / 2.0;                              // :139
+    features.energyEnvelope.setSize (1, n_frames);                                     // :140
+    std::vector<float> temp ((size_t) 2 * N);                // (the reference's float temp[4096] is too small for its own call at N > 2048)
+    std::vector<int> numPeaks ((size_t) n_frames, 0);
+    for (int frame = 0; frame < n_frames; ++frame)
+    {
+        analyser.fftIn.clear();                                                         // :144
+        int rangeStart = -numFFTInputSamples / 2, rangeEnd = numFFTInputSamples / 2, offsetToAdd = numFFTInputSamples / 2;   // :150-152
+        if (n_frames == 1) { rangeStart = 0; rangeEnd = numFFTInputSamples; offsetToAdd = 0; }                               // :155-161
+        for (int sample = rangeStart; sample < rangeEnd; ++sample)                      // :165-179
+        {
+            const int i = frame * stepSize + sample;
+            if (i < 0 || i >= numInputSamples) analyser.fftIn.getWritePointer (0)[sample + numFFTInputSamples / 2] = 0.0f;
+            else                               analyser.fftIn.getWritePointer (0)[sample + offsetToAdd] = features.audioOutput.getReadPointer (0)[i];
+        }
+        AudioAnalyser::scaleBufferWithBartlettWindowing (analyser.fftIn);              // :181
+        for (int i = 0; i < N; ++i) { temp[(size_t) i] = analyser.fftIn.getReadPointer (0)[i]; temp[(size_t) (N + i)] = 0.0f; }
+        analyser.fft.performFrequencyOnlyForwardTransform (temp.data());                // :208 / :224
+        for (int i = 0; i <= N / 2; ++i) analyser.fftOut.setSample (0, i, temp[(size_t) i]);          // :226-227: N/2 + 1 amplitudes
+        float* o = out + (long) frame * FXL_NUM;
+        const AudioAnalyser::SpectralCharacteristics sc = analyser.calculateSpectralCharacteristics (analyser.fftOut, 0);   // :231
+        o[FXL_CENTROID] = sc.centroid; o[FXL_SPREAD] = sc.spread; o[FXL_FLATNESS] = sc.flatness; o[FXL_FLUX] = sc.flux;   // :232-235
+        o[FXL_SLOPE] = analyser.calculateNormalisedSpectralSlope (analyser.fftOut, 0);                                        // :236
+        {
+            // (the peak count is a diagnostic: the same test calculateHarmonicCharacteristics applies, :361-369)
+            double sum = 0.0;
+            for (int b = 0; b <= N / 2; ++b) sum += (double) analyser.fftOut.getSample (0, b);
+            int np = 0;
+            if (! (sum < 0.001)) for (int b = 0; b <= N / 2; ++b) np += analyser.binIsPeak (b, analyser.fftOut, 0, sum / (double) (N / 2 + 1)) ? 1 : 0;
+            numPeaks[(size_t) frame] = np;
+        }
+        const AudioAnalyser::HarmonicCharacteristics hc = analyser.calculateHarmonicCharacteristics (analyser.fftOut, 0);   // :242
+        o[FXL_F0] = hc.f0; o[FXL_HER] = hc.harmonicEnergyRatio; o[FXL_INHARM] = hc.inharmonicity;                          // :243-245
+        o[FXL_NUM_PEAKS] = (float) numPeaks[(size_t) frame];
+        features.energyEnvelope.setSample (0, frame, AudioAnalyser::sumAccrossChannels (analyser.fftOut));                   // :249
+        o[FXL_ENERGY] = features.energyEnvelope.getSample (0, frame);
+    }
+    analyser.analyseNormalisedZeroCrosses (features);                                   // :517-541
+    for (int frame = 0; frame < n_frames; ++frame)
+        out[(long) frame * FXL_NUM + FXL_ZCR] = features.getFeatureSample (ConcatenatedFeatureBuffer::ZeroCrosses, 0, frame);
+    analyser.setLogAttackTime (features);                                               // :611-622
+    if (log_attack != nullptr) *log_attack = features.estimatedLogAttackTime;
+    return n_frames;
 }
 
 void fxo_fft_forward (const float* frame, int n, float* out_2n)

