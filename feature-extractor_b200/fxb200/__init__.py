@@ -34,7 +34,11 @@ EXPORTS = (
     "fx_pcm_bytes_per_sample", "fx_analyse_host_pcm", "fx_decode_pcm_device",
     "fx_poll_block", "fx_rt_start", "fx_rt_stop", "fx_set_features_callback", "fx_set_track_active", "fx_clear_buffer",
     "fx_set_sample_rate", "fx_rt_get_stats", "fx_osc_encode_tracks", "fx_synth_device_at", "fx_h2d_probe",
+    "fx_legacy_analyse_host",
 )
+
+# fx_engine.h FX_LEGACY_*: output slots of the legacy offline analyser (AudioAnalysis.h)
+LEGACY = ("centroid", "spread", "flatness", "flux", "slope", "f0", "her", "inharm", "zcr", "energy", "num_peaks", "product_state")
 
 # fx_engine.h FX_PCM_*: sample encodings of WAV (little endian) and AIFF (big endian) data chunks
 PCM_FORMATS = {"u8": 1, "s8": 2, "s16le": 3, "s16be": 4, "s24le": 5, "s24be": 6, "s32le": 7, "s32be": 8, "f32le": 9, "f32be": 10}
@@ -140,6 +144,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.fx_synth_device_at.restype = c_int
     lib.fx_h2d_probe.argtypes = [c_int, c_long, c_int, c_int, POINTER(c_double)]
     lib.fx_h2d_probe.restype = c_int
+    lib.fx_legacy_analyse_host.argtypes = [c_int, c_int, c_double, c_void_p, c_long, c_long, c_int, c_int, c_void_p, c_void_p]
+    lib.fx_legacy_analyse_host.restype = c_int
     if path is None:
         _lib = lib
     return lib
@@ -372,6 +378,20 @@ def measure_fp32_peak(device: int = 0) -> float:
     if st != 0:
         raise FxError(f"fx_measure_fp32_peak failed ({st})")
     return tf.value
+
+
+def legacy_analyse(audio: np.ndarray, n_frames: int, window: int = 2048, sample_rate: float = 48000.0, device: int = 0):
+    """The legacy offline analyser (AudioAnalysis.h AudioAnalyser) on the GPU: audio float32 [n_tracks, n_samples] ->
+    (features [n_tracks, n_frames, 12] in LEGACY order, log attack time [n_tracks])."""
+    lib = load_library()
+    a = np.ascontiguousarray(np.atleast_2d(audio), dtype=np.float32)
+    T, S = a.shape
+    out = np.zeros((T, n_frames, len(LEGACY)), np.float32)
+    la = np.zeros(T, np.float32)
+    st = lib.fx_legacy_analyse_host(device, window, sample_rate, a.ctypes.data, S, S, T, n_frames, out.ctypes.data, la.ctypes.data)
+    if st != 0:
+        raise FxError(f"fx_legacy_analyse_host failed ({st})")
+    return out, la
 
 
 def h2d_probe(device: int = 0, nbytes: int = 1 << 30, reps: int = 4, write_combined: bool = False) -> float:

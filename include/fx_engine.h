@@ -221,6 +221,30 @@ fx_status   fx_osc_encode_tracks (fx_engine* e, const int* tracks, int n_tracks,
  * n_out = 12 (as the code sends) or 10 (as README.md:55-57 documents). */
 fx_status   fx_osc_order (const float in12[FX_NUM_FEATURES], float* out, int n_out);
 
+/* ---- legacy offline analyser ----------------------------------------------------
+ * struct AudioAnalyser of AudioAnalysis.h: the per-frame pipeline of performSpectralAnalysis (:121-251) with the feature
+ * block that the reference has commented out at its own call site (:219-247) reinstated -- frame i centred on sample
+ * i * stepSize (stepSize = n_samples / n_frames, :130), zero padded, symmetric Bartlett ramps (:663-672), TRUE magnitudes
+ * of bins 0 .. N/2 (performFrequencyOnlyForwardTransform :208, :226-227), then calculateSpectralCharacteristics (:463-515),
+ * calculateNormalisedSpectralSlope (:566-609), calculateHarmonicCharacteristics (:253-306: histogram of peak intervals,
+ * previousF0 hysteresis :279-298, inharmonicity :308-338), the energy envelope (:249), analyseNormalisedZeroCrosses (:517-541)
+ * and setLogAttackTime (:611-622).  The application never instantiates AudioAnalyser; this entry point exists for callers
+ * of that class.  audio is [n_tracks][track_stride] fp32 HOST memory (one channel per track); out is
+ * [n_tracks][n_frames][FX_LEGACY_NUM]; log_attack [n_tracks] (may be NULL).  Self-contained: needs no fx_engine. */
+enum {
+    FX_LEGACY_CENTROID = 0,   /* centroid / nyquist (:514) */
+    FX_LEGACY_SPREAD, FX_LEGACY_FLATNESS, FX_LEGACY_FLUX, FX_LEGACY_SLOPE,
+    FX_LEGACY_F0,             /* Hz, after the previousF0 rule */
+    FX_LEGACY_HER, FX_LEGACY_INHARM,
+    FX_LEGACY_ZCR,            /* zero crossings * 2 / stepSize (:538) */
+    FX_LEGACY_ENERGY,         /* energy envelope (:249) */
+    FX_LEGACY_NUM_PEAKS,      /* diagnostic: peak bins of the frame (:366-387) */
+    FX_LEGACY_PRODUCT_STATE,  /* diagnostic: the ungated fp64 product (:491): 0 finite, 1 reached 0, 2 reached inf, 3 ended denormal, 4 frame silent */
+    FX_LEGACY_NUM
+};
+fx_status   fx_legacy_analyse_host (int device, int window, double sample_rate, const float* audio, long track_stride,
+                                    long n_samples, int n_tracks, int n_frames, float* out, float* log_attack);
+
 /* ---- measurement support (bench.py; not part of the reference surface) -------------------------------
  * Fill d_audio [n_tracks][track_stride] with the synthetic workload of SURVEY.md section 8d:
  * A sin(2 pi f_t n / sr + phi_t) + sigma_t u_t[n], Philox-4x32-10 keyed by (seed, track), with the

@@ -800,3 +800,251 @@ long fxo_pcm_decode (const void* pcm, int format, int n_channels, int channel, l
     }
     return n_samples;
 }
+
+/* ================================================================================================
+ * Legacy offline analyser -- AudioAnalysis.h (struct AudioAnalyser), restated.  See fx_oracle_api.h for what is driven
+ * and why (the feature block is commented out at the reference's own call site, :219-247; the member functions are
+ * intact).  Pinned bit for bit against oracle/_ref (the reference's own functions) in tests/test_legacy.py.
+ * Slot FXL_MARGIN (this port only; oracle/_ref reports -1) is the smallest relative margin of the decisions that feed the
+ * harmonic features of the frame: peak tests (:366-381), the choice of the histogram's best candidate (:428-433), the
+ * previousF0 hysteresis (:279-298), the silence gates (:271, :497, :575).
+ * ================================================================================================ */
+typedef struct { int interval, count; double her, freq; } l_cand;
+
+static double l_ratio (double f1, double f2)                                       /* getFrequencyRatio :340-348 */
+{
+    double higher, lower;
+    if (f1 == f2) return 1.0;
+    higher = f1 > f2 ? f1 : f2;
+    lower = higher == f1 ? f2 : f1;
+    return higher / lower;
+}
+
+/* F0Candidate::updateHarmonicEnergyRatio :79-98 */
+static double l_her (const float* mag, int nb, double frequency, double frpb, double total, double num_harmonics)
+{
+    double score = 0.0, harmonic;
+    for (harmonic = 1.0; harmonic < num_harmonics + 1.0; harmonic++) {
+        const double hf = frequency * harmonic;
+        const int bin = (int) (ceil (hf / frpb));
+        if (bin >= nb) break;
+        score += (double) mag[bin];
+    }
+    return score / total;
+}
+
+static int l_is_peak (const float* mag, int nb, int bin, double mean, float* margin)     /* binIsPeak :366-387 */
+{
+    const double m = (double) mag[bin];
+    int left, right, n;
+    margin_min (margin, relmargin (m, mean));
+    if (m <= mean) return 0;
+    left = bin < 2 ? 2 - bin : 0;
+    right = bin >= nb - 2 ? 2 - ((nb - 1) - bin) : 0;
+    for (n = bin - (2 - left); n < bin + (2 - right); n++) {
+        const double nm = (double) mag[n];
+        if (n != bin) margin_min (margin, relmargin (nm, m));
+        if (n != bin && nm > m) return 0;
+    }
+    return 1;
+}
+
+long fxo_legacy_analyse (int window, double sample_rate, const float* audio, long n_samples, int n_frames,
+                         float* out, float* log_attack)
+{
+    const int N = window, nb = N / 2 + 1;
+    const double nyquist = sample_rate / 2.0;
+    const double frpb = nyquist / (double) nb;
+    fft_plan plan;
+    float *fft_in, *temp, *mag, *envelope;
+    cpx* scratch;
+    double* prev;
+    int* peaks;
+    l_cand* hist;
+    double previous_f0 = 0.0;
+    int frame, i, step;
+    if (N < 16 || (N & (N - 1)) != 0 || n_frames < 1 || n_samples < n_frames) return -1;
+    step = (int) (n_samples / n_frames);                                          /* :130 */
+    fft_plan_init (&plan, N, 0);
+    fft_in = (float*) calloc ((size_t) N, sizeof (float));
+    temp = (float*) calloc ((size_t) 2 * N, sizeof (float));
+    mag = (float*) calloc ((size_t) nb, sizeof (float));
+    envelope = (float*) calloc ((size_t) n_frames, sizeof (float));
+    scratch = (cpx*) calloc ((size_t) N, sizeof (cpx));
+    prev = (double*) calloc ((size_t) nb, sizeof (double));                       /* previousBinMagnitudes, zeros (:115-116) */
+    peaks = (int*) calloc ((size_t) nb, sizeof (int));
+    hist = (l_cand*) calloc ((size_t) nb + 1, sizeof (l_cand));
+
+    for (frame = 0; frame < n_frames; ++frame) {
+        float* o = out + (long) frame * FXL_NUM;
+        float margin = 1.0f;
+        int range_start = -N / 2, range_end = N / 2, offset = N / 2, s;
+        memset (fft_in, 0, (size_t) N * sizeof (float));                          /* :144 */
+        if (n_frames == 1) { range_start = 0; range_end = N; offset = 0; }        /* :155-161 */
+        for (s = range_start; s < range_end; ++s) {                               /* :165-179 */
+            const long k = (long) frame * step + s;
+            if (k < 0 || k >= n_samples) fft_in[s + N / 2] = 0.0f;
+            else fft_in[s + offset] = audio[k];
+        }
+        /* scaleBufferWithBartlettWindowing :663-672: two applyGainRamp calls, gain accumulated additively in fp32 */
+        {
+            float g = 0.0f; const float inc = (1.0f - 0.0f) / (float) (N / 2);
+            for (i = 0; i < N / 2; ++i) { fft_in[i] *= g; g += inc; }
+            g = 1.0f;
+            { const float dec = (0.0f - 1.0f) / (float) (N / 2); for (i = 0; i < N / 2; ++i) { fft_in[N / 2 + i] *= g; g += dec; } }
+        }
+        /* FFT::performFrequencyOnlyForwardTransform (:208) [JUCE-recall]: full complex transform, then juce_hypot per bin */
+        for (i = 0; i < N; ++i) { temp[i] = fft_in[i]; temp[N + i] = 0.0f; }
+        fft_real_forward (&plan, temp, scratch);
+        for (i = 0; i < nb; ++i) mag[i] = (float) sqrt ((double) temp[2 * i] * temp[2 * i] + (double) temp[2 * i + 1] * temp[2 * i + 1]);
+
+        /* ---- calculateSpectralCharacteristics :463-515 ------------------------------------------------ */
+        {
+            double weighted = 0.0, var = 0.0, sum = 0.0, product = 1.0, flux = 0.0;
+            for (i = 0; i < nb; ++i) {
+                const double fc = (double) i * frpb + (frpb / 2.0);
+                const double m = (double) mag[i];
+                const double diff = fabs (m) - fabs (prev[i]);
+                const double rect = (diff + fabs (diff)) / 2.0;
+                if (diff > 0.0) flux += rect;
+                sum += m;
+                product *= m;
+                weighted += fc * m;
+            }
+            margin_min (&margin, relmargin (sum, 0.001));
+            if (! (sum > 0.001)) { o[FXL_CENTROID] = o[FXL_SPREAD] = o[FXL_FLATNESS] = o[FXL_FLUX] = 0.0f; }
+            else {
+                const float centroid = (float) (weighted / sum);
+                const double inv = 1.0 / (double) nb;
+                const float flatness = (float) (pow (product, inv) / (inv * sum));
+                float max_spread;
+                for (i = 0; i < nb; ++i) {
+                    const double fc = (double) i * frpb + (frpb / 2.0);
+                    var += pow ((fc / nyquist) - (centroid / nyquist), 2.0) * (double) mag[i];
+                    prev[i] = (double) mag[i];
+                }
+                max_spread = (float) ((centroid / nyquist) * (1.0 - (centroid / nyquist)));
+                o[FXL_CENTROID] = centroid / (float) nyquist;
+                o[FXL_SPREAD] = (float) ((var / sum) / max_spread);
+                o[FXL_FLATNESS] = flatness;
+                o[FXL_FLUX] = (float) flux;
+            }
+        }
+        /* ---- calculateNormalisedSpectralSlope :566-609 ------------------------------------------------- */
+        {
+            const double num_bins = (double) nb, mean_bin = 0.5;
+            double mean_energy = 0.0, prod_sum = 0.0, bin_var = 0.0, energy_var = 0.0, di;
+            float mx = 0.0f;
+            for (i = 0; i < nb; ++i) { const float a = fabsf (mag[i]); if (a > mx) mx = a; }       /* getMagnitude */
+            margin_min (&margin, relmargin ((double) mx, 0.0001));
+            if (! ((double) mx > 0.0001)) o[FXL_SLOPE] = 0.0f;
+            else {
+                const double fm = (double) mx;
+                double bin_std, energy_std, r;
+                for (i = 0; i < nb; ++i) { const double e = mag[i] / fm; mean_energy += e; prod_sum += (double) i * e; }
+                mean_energy /= num_bins;
+                for (di = 0.0; di < num_bins; di++) {
+                    const double ni = di / num_bins;
+                    const double e = mag[(int) di] / fm;
+                    bin_var += (ni - mean_bin) * (ni - mean_bin);
+                    energy_var += (e - mean_energy) * (e - mean_energy);
+                }
+                bin_var /= num_bins; energy_var /= num_bins;
+                bin_std = sqrt (bin_var); energy_std = sqrt (energy_var);
+                r = (prod_sum - (num_bins * mean_energy * mean_bin)) / (num_bins - 1.0f) * energy_std * bin_std;
+                o[FXL_SLOPE] = (float) (r * (bin_std / energy_std));
+            }
+        }
+        /* ---- calculateHarmonicCharacteristics :253-306 ------------------------------------------------- */
+        {
+            double sum = 0.0, mean;
+            int n_peaks = 0, n_hist = 0;
+            o[FXL_F0] = o[FXL_HER] = o[FXL_INHARM] = 0.0f; o[FXL_NUM_PEAKS] = 0.0f;
+            for (i = 0; i < nb; ++i) sum += (double) mag[i];
+            mean = sum / (double) nb;
+            margin_min (&margin, relmargin (sum, 0.001));
+            if (! (sum < 0.001)) {
+                double f0 = 0.0, her = 0.0, max_weighted = 0.0, second_weighted = 0.0, inharm = 0.0;
+                int b, p, c;
+                /* fillPeakBinsAndFrequencyHistogram :350-363, addNewPeakBinAndUpdateHistogram :389-403 */
+                for (b = 0; b < nb; ++b) {
+                    if (! l_is_peak (mag, nb, b, mean, &margin)) continue;
+                    peaks[n_peaks++] = b;
+                    for (p = 0; p < n_peaks - 1; ++p) {
+                        const int interval = b - peaks[p];
+                        int pos = -1;
+                        for (c = 0; c < n_hist; ++c) if (hist[c].interval == interval) { pos = c; break; }
+                        if (pos != -1) hist[pos].count++;
+                        else { hist[n_hist].interval = interval; hist[n_hist].count = 1; n_hist++; }
+                    }
+                }
+                /* estimateF0AndHERFromFrequencyHistogram :415-436 */
+                for (c = 0; c < n_hist; ++c) {
+                    double w;
+                    hist[c].freq = (double) hist[c].interval * frpb;
+                    hist[c].her = l_her (mag, nb, hist[c].freq, frpb, sum, 15.0);
+                    w = (double) hist[c].count * hist[c].her;
+                    if (w > max_weighted) { second_weighted = max_weighted; max_weighted = w; f0 = hist[c].freq; her = hist[c].her; }
+                    else if (w > second_weighted) second_weighted = w;
+                }
+                if (n_hist > 0) margin_min (&margin, relmargin (max_weighted, second_weighted));
+                /* previousF0 hysteresis :279-298 */
+                if (previous_f0 != f0 && previous_f0 > 10.0) {
+                    const double top = previous_f0 > f0 ? previous_f0 : f0;
+                    const double bottom = top == previous_f0 ? f0 : previous_f0;
+                    const double ratio = top / bottom;
+                    margin_min (&margin, relmargin (ratio, 2.0));
+                    if (ratio > 2.0) {
+                        const double frac = ratio - floor (ratio);
+                        margin_min (&margin, relmargin (frac, 0.1));
+                        if (frac < 0.1) { f0 = previous_f0; her = l_her (mag, nb, f0, frpb, sum, 15.0); }
+                    }
+                }
+                previous_f0 = f0;
+                /* calculateInharmonicity :308-338 */
+                if (f0 > 0.0) {
+                    const int f0_bin = (int) (ceil (f0 / frpb));                    /* getBinForFrequency :438-443 */
+                    for (p = 0; p < n_peaks; ++p) {
+                        const int bin = peaks[p];
+                        double start, end, ra, rb, r;
+                        if (f0_bin == bin) continue;
+                        start = bin * frpb;
+                        if (start == 0.0) start = frpb * 0.5;
+                        end = (double) (bin + 1) * frpb;
+                        ra = l_ratio (start, f0); rb = l_ratio (end, f0);
+                        if (floor (ra) != floor (rb)) continue;
+                        r = ra < rb ? ra : rb;
+                        inharm += (r - floor (r)) * ((double) mag[bin] / sum);
+                    }
+                }
+                o[FXL_F0] = (float) f0; o[FXL_HER] = (float) her; o[FXL_INHARM] = (float) inharm; o[FXL_NUM_PEAKS] = (float) n_peaks;
+            }
+        }
+        /* energy envelope :249 (sumAccrossChannels: fp32 running sum in bin order) */
+        { float e = 0.0f; for (i = 0; i < nb; ++i) e += mag[i]; envelope[frame] = e; o[FXL_ENERGY] = e; }
+        o[FXL_MARGIN] = margin;
+    }
+    /* analyseNormalisedZeroCrosses :517-541 */
+    for (frame = 0; frame < n_frames; ++frame) {
+        float crosses = 0.0f;
+        const long base = (long) frame * step;
+        int s;
+        for (s = 0; s < step - 1; ++s) {
+            const float first = audio[base + s], second = audio[base + s + 1];
+            if ((first > 0.0f && (first - second) > first) || (first < 0.0f && (first - second) < first)) crosses++;
+        }
+        out[(long) frame * FXL_NUM + FXL_ZCR] = crosses * 2.0f / (float) step;
+    }
+    /* setLogAttackTime :611-622 */
+    if (log_attack != NULL) {
+        float mx = envelope[0];
+        const double ms_per_sample = 1.0 / (double) ((int) sample_rate / 1000);
+        for (i = 1; i < n_frames; ++i) if (envelope[i] > mx) mx = envelope[i];
+        i = 0;
+        while (i < n_frames && envelope[i] != mx) i++;
+        *log_attack = (float) (log10 ((double) (float) (i * step) * (float) ms_per_sample));
+    }
+    fft_plan_free (&plan);
+    free (fft_in); free (temp); free (mag); free (envelope); free (scratch); free (prev); free (peaks); free (hist);
+    return n_frames;
+}

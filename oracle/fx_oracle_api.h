@@ -92,6 +92,7 @@ enum {
     FXL_ZCR,            /* zero crossings * 2 / stepSize            (:538) */
     FXL_ENERGY,         /* energy envelope: sum of the frame's magnitudes (:249) */
     FXL_NUM_PEAKS,      /* diagnostics: number of peak bins (:361-369) */
+    FXL_MARGIN,         /* diagnostics: smallest relative margin of the frame's decisions (port only, else -1) */
     FXL_NUM
 };
 long fxo_legacy_analyse (int window, double sample_rate, const float* audio, long n_samples, int n_frames,

@@ -282,6 +282,7 @@ long fxo_legacy_analyse (int window, double sample_rate, const float* audio, lon
         const AudioAnalyser::HarmonicCharacteristics hc = analyser.calculateHarmonicCharacteristics (analyser.fftOut, 0);   // :242
         o[FXL_F0] = hc.f0; o[FXL_HER] = hc.harmonicEnergyRatio; o[FXL_INHARM] = hc.inharmonicity;                          // :243-245
         o[FXL_NUM_PEAKS] = (float) numPeaks[(size_t) frame];
+        o[FXL_MARGIN] = -1.0f;
         features.energyEnvelope.setSample (0, frame, AudioAnalyser::sumAccrossChannels (analyser.fftOut));                   // :249
         o[FXL_ENERGY] = features.energyEnvelope.getSample (0, frame);
     }

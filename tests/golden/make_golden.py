@@ -43,5 +43,19 @@ def main():
         print(name, r["raw"].shape)
 
 
+def legacy():
+    """the legacy offline analyser (AudioAnalysis.h AudioAnalyser) driven headless: tests/test_legacy.py"""
+    if not os.path.exists(ou.REF_SO):
+        raise SystemExit("oracle/_ref/libfxref.so missing")
+    N, sr, T, F, first = 2048, 48000.0, 6, 150, 2
+    S = int(sr * 4.0)
+    audio = ou.make_tracks(T, S, sr, first_track=first)
+    out, la = ou.legacy_analyse(ou.REF_SO, audio, F, N, sr)
+    np.savez_compressed(os.path.join(HERE, "legacy_n2048_sr48000.npz"), window=N, sample_rate=sr, n_tracks=T, n_samples=S, n_frames=F,
+                        first_track=first, audio_head=audio[:, :64], out=out, log_attack=la)
+    print("legacy", out.shape)
+
+
 if __name__ == "__main__":
     main()
+    legacy()

@@ -87,6 +87,26 @@ class Oracle:
         return b
 
 
+# legacy offline analyser (AudioAnalysis.h AudioAnalyser): output slots of fxo_legacy_analyse
+L = {n: i for i, n in enumerate(("centroid", "spread", "flatness", "flux", "slope", "f0", "her", "inharm", "zcr", "energy", "num_peaks", "margin"))}
+
+
+def legacy_analyse(lib_path: str, audio: np.ndarray, n_frames: int, window: int = 2048, sample_rate: float = 48000.0):
+    """fxo_legacy_analyse of one checker (PORT_SO or REF_SO) on every row of audio: ([T, n_frames, 12], log attack [T])."""
+    lib = ctypes.CDLL(lib_path)
+    lib.fxo_legacy_analyse.restype = ctypes.c_long
+    lib.fxo_legacy_analyse.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    a = np.ascontiguousarray(np.atleast_2d(audio), dtype=np.float32)
+    out = np.zeros((a.shape[0], n_frames, len(L)), np.float32)
+    la = np.zeros(a.shape[0], np.float32)
+    for t in range(a.shape[0]):
+        v = ctypes.c_float(0)
+        n = lib.fxo_legacy_analyse(window, sample_rate, a[t].ctypes.data, a.shape[1], n_frames, out[t].ctypes.data, ctypes.byref(v))
+        assert n == n_frames, n
+        la[t] = v.value
+    return out, la
+
+
 def port() -> Oracle:
     if not os.path.exists(PORT_SO):
         build_oracle()

@@ -13,5 +13,5 @@ cp $ROOT/include/fx_engine.h $W/include/
 mkdir -p $ROOT/feature-extractor_b200/lib/exp
 cd $W/feature-extractor_b200
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared $2 \
-  -o $ROOT/feature-extractor_b200/lib/exp/libfxb200_$name.so csrc/fx_analyse.cu csrc/fx_post.cu csrc/fx_pcm.cu csrc/fx_tables.cu csrc/fx_engine.cu -lcudart -lpthread
+  -o $ROOT/feature-extractor_b200/lib/exp/libfxb200_$name.so csrc/fx_analyse.cu csrc/fx_post.cu csrc/fx_pcm.cu csrc/fx_tables.cu csrc/fx_legacy.cu csrc/fx_engine.cu -lcudart -lpthread
 echo built $name
