@@ -110,6 +110,27 @@ def main():
     add("c5", f"configs[4] stream length: {a.shape[0]} tracks x {a.shape[1] / sr / 60:g} min ({a.shape[1] // H} frames/track) in 60 carried calls, N=2048 H=1024",
         engine_carried(a, N, H, sr, 60), ora.analyse(a, window=N, hop=H, sample_rate=sr))
 
+    # row f4: the legacy offline analyser (AudioAnalysis.h member functions), its own comparison rule (tests/test_legacy.py)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_legacy as tl
+
+    N, sr = 2048, 48000.0
+    a = ou.make_tracks(4 if q else 24, int(sr * (2.0 if q else 8.0)), sr)
+    F = 90 if q else 375
+    g, la_g = fxb200.legacy_analyse(a, F, N, sr)
+    pv, la_p = ou.legacy_analyse(ou.PORT_SO, a, F, N, sr)
+    if os.path.exists(ou.REF_SO):
+        ov, la_o = ou.legacy_analyse(ou.REF_SO, a, F, N, sr)
+        assert np.array_equal(ov[..., :11], pv[..., :11], equal_nan=True)
+    else:
+        ov, la_o = pv, la_p
+    res = tl.compare_legacy(g, la_g, ov, la_o, pv[..., ou.L["margin"]])
+    res["what"] = f"legacy offline analyser: {a.shape[0]} tracks x {a.shape[1] / sr:g} s, N=2048, {F} frames per track, values from oracle/_ref, margins from the port"
+    fin = np.isfinite(g[..., :10]) & np.isfinite(ov[..., :10])
+    res["max_abs_err"] = {n: float(np.abs(np.where(fin[..., i], g[..., i].astype(np.float64) - ov[..., i], 0.0)).max()) for n, i in list(ou.L.items())[:10]}
+    report["legacy_f4"] = res
+    print("legacy_f4", {k: v for k, v in res.items() if k != "max_abs_err"}, flush=True)
+
     tot = {k: sum(c[k] for c in report["configs"].values()) for k in ("frames", "raw_mismatch_total", "raw_mismatch_exempt", "bad_raw", "lag_mismatch", "bad_lag", "bad_smooth", "gpu_only_low_margin_frames")}
     tot["exempt_by_cause"] = {c: sum(v["exempt_by_cause"][c] for v in report["configs"].values()) for c in ou.CAUSES}
     tot["max_abs_err"] = {n: max(v["max_abs_err"][n] for v in report["configs"].values()) for n in ou.F}
@@ -117,7 +138,8 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(report, open(args.out, "w"), indent=1)
     print("totals", {k: v for k, v in tot.items() if k != "max_abs_err"})
-    sys.exit(0 if tot["bad_raw"] == 0 and tot["bad_lag"] == 0 and tot["bad_smooth"] == 0 else 1)
+    ok = tot["bad_raw"] == 0 and tot["bad_lag"] == 0 and tot["bad_smooth"] == 0 and res["bad_continuous"] == 0 and res["bad_harmonic"] == 0
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
