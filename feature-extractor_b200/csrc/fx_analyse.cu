@@ -38,6 +38,15 @@
 #ifndef FX_SINGLE_PASS
 #define FX_SINGLE_PASS 1
 #endif
+// FX_WARMUP_ALL_LANES 1: the filter's cross-warp warm-up is computed by every lane from broadcast loads (an independent chain
+//   next to the recurrence) instead of by lane 0 in a divergent tail: same values, -0.4 % kernel time (0 restores the branch).
+// FX_TW2_PREFETCH 1 (experiment, off): stage-2 twiddles loaded before the block barrier inside the transform: +2.2 % (spills).
+#ifndef FX_TW2_PREFETCH
+#define FX_TW2_PREFETCH 0
+#endif
+#ifndef FX_WARMUP_ALL_LANES
+#define FX_WARMUP_ALL_LANES 1
+#endif
 
 namespace fx {
 
@@ -257,6 +266,16 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
     Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
     const int t = threadIdx.x;
     fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1, sm.tw1f);
+#if FX_TW2_PREFETCH
+    float2 tw[15];
+    #pragma unroll
+    for (int k = 0; k < 15; ++k) tw[k] = sm.tw2[k * 16 + (t & 15)];
+    __syncthreads();
+    fft_stage2_tw<R1, false> (t, sm.ex, tw);
+    __syncwarp();
+    fft_stage3<R1, false> (t, sm.ex);
+    return;
+#endif
     __syncthreads();
 #if FX_STAGE23_SHFL
     fft_stage23_shfl<R1, false> (t, sm.ex, sm.tw2);         // experiment: the 2 -> 3 exchange by warp shuffles (measured slower)
@@ -401,6 +420,23 @@ k_analyse (const AnalyseParams p)
             ys[0] = y;
             #pragma unroll
             for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (xs[j], c1g)); ys[j] = y; }
+#if FX_WARMUP_ALL_LANES
+            // every lane runs the warm-up of its WARP's first segment from broadcast loads (one wavefront each): an independent
+            // chain the scheduler can interleave with the recurrence above, instead of a divergent tail behind it
+            float ywarm = 0.0f;
+            {
+                const int rpw = (int) ((a0 + 16 * (t & ~31) - 12) & (N - 1));
+                #pragma unroll
+                for (int q = 0; q < 3; ++q)
+                {
+                    const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[rpw + 4 * q]);
+                    ywarm = fmaf (c2, ywarm, __fmul_rn (x4.x, c1g)); ywarm = fmaf (c2, ywarm, __fmul_rn (x4.y, c1g));
+                    ywarm = fmaf (c2, ywarm, __fmul_rn (x4.z, c1g)); ywarm = fmaf (c2, ywarm, __fmul_rn (x4.w, c1g));
+                }
+            }
+            float yin = __shfl_up_sync (0xffffffffu, y, 1);
+            if (lane == 0) yin = (t != 0) ? ywarm : 0.0f;
+#else
             float yin = __shfl_up_sync (0xffffffffu, y, 1);
             if (lane == 0)
             {
@@ -418,6 +454,7 @@ k_analyse (const AnalyseParams p)
                     }
                 }
             }
+#endif
             // e^(-pi/2 (j+1)): the filter constant is fixed by AudioFilter::m = 2 (RealTimeAudioAnalysis.h:127)
             constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
                                            8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,

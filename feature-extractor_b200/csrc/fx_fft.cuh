@@ -233,6 +233,28 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     }
 }
 
+// Stage 2 with its 15 twiddles already in registers (loaded by the caller BEFORE the block barrier that separates stage 1
+// from stage 2, while stage 1's values are dead and the registers free).
+template <int R1, bool INV>
+__device__ __forceinline__ void fft_stage2_tw (int t, float2* __restrict__ ex, const float2* tw)
+{
+    using D = FftDims<R1>;
+    const int k1 = t >> 4, n3 = t & 15;
+    float2* row = ex + k1 * D::ROW + n3;
+    float2 v[16];
+    #pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
+    butterfly<16, INV> (v);
+    #pragma unroll
+    for (int s = 0; s < 16; ++s)
+    {
+        const int k2 = out_index<16> (s);
+        float2 val = v[s];
+        if (k2 > 0) val = cmulw<INV> (val, tw[k2 - 1]);
+        row[k2 * 17] = val;
+    }
+}
+
 // Stage 3 in place: X[k1 + R1 k2 + 16 R1 k3] replaces element (k2, n3 = k3) of row k1.  The caller has made the stage-2
 // stores of this half warp visible (__syncwarp).
 template <int R1, bool INV>
