@@ -26,6 +26,13 @@
                             //    1.7 % faster); 0: product of two small shared-memory factors (two loads and a complex multiply)
 #endif
 
+// EXPERIMENT (FX_TW_POWERS=1): only the twiddles W^1, W^2, W^4, W^8 of a thread are loaded (exact table values); the other
+// eleven are products of those, at most three multiplications deep (W^15 = W^8 W^4 W^2 W^1): 11 packed complex multiplies in
+// place of 11 loads per stage and transform.  The loads ride the L1 / shared-memory data pipe, the busiest unit of the kernel.
+#ifndef FX_TW_POWERS
+#define FX_TW_POWERS 0
+#endif
+
 namespace fx {
 
 __device__ __forceinline__ int phys (int a) { return a + (a >> 4); }
@@ -165,6 +172,23 @@ __device__ __forceinline__ void butterfly (float2* v)
     }
 }
 
+// w[k] = w1^k for k = 1 .. R - 1 from the exact values of w1^1, w1^2, w1^4, w1^8 (slots 1, 2, 4, 8 filled by the caller)
+template <int R>
+__device__ __forceinline__ void twiddle_powers (float2* w)
+{
+    w[3] = cmulw<false> (w[2], w[1]);
+    if (R > 4)
+    {
+        w[5] = cmulw<false> (w[4], w[1]); w[6] = cmulw<false> (w[4], w[2]); w[7] = cmulw<false> (w[4], w[3]);
+    }
+    if (R > 8)
+    {
+        w[9]  = cmulw<false> (w[8], w[1]); w[10] = cmulw<false> (w[8], w[2]); w[11] = cmulw<false> (w[8], w[3]);
+        w[12] = cmulw<false> (w[8], w[4]); w[13] = cmulw<false> (w[8], w[5]); w[14] = cmulw<false> (w[8], w[6]);
+        w[15] = cmulw<false> (w[8], w[7]);
+    }
+}
+
 // Shared-memory footprint helpers (in elements)
 template <int R1> struct FftDims
 {
@@ -192,6 +216,13 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
 #if ! FX_TW1_GLOBAL
         const int mh = m >> 4, ml = 16 + (m & 15);
 #endif
+#if FX_TW_POWERS
+        float2 wp[16];
+        wp[1] = __ldg (&tw1f[m]); wp[2] = __ldg (&tw1f[256 + m]);
+        if (R1 > 4) wp[4] = __ldg (&tw1f[3 * 256 + m]);
+        if (R1 > 8) wp[8] = __ldg (&tw1f[7 * 256 + m]);
+        twiddle_powers<R1> (wp);
+#endif
         #pragma unroll
         for (int s = 0; s < R1; ++s)
         {
@@ -199,7 +230,9 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
             float2 val = v[q * R1 + s];
             if (k1 > 0)
             {
-#if FX_TW1_GLOBAL
+#if FX_TW_POWERS
+                const float2 w = wp[k1];
+#elif FX_TW1_GLOBAL
                 const float2 w = __ldg (&tw1f[(k1 - 1) * 256 + m]);
 #else
                 const float2 wa = tw1[(k1 - 1) * 32 + mh], wb = tw1[(k1 - 1) * 32 + ml];
@@ -223,12 +256,21 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
     butterfly<16, INV> (v);
+#if FX_TW_POWERS
+    float2 wp[16];
+    wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[3 * 16 + n3]; wp[8] = tw2[7 * 16 + n3];
+    twiddle_powers<16> (wp);
+#endif
     #pragma unroll
     for (int s = 0; s < 16; ++s)
     {
         const int k2 = out_index<16> (s);
         float2 val = v[s];
+#if FX_TW_POWERS
+        if (k2 > 0) val = cmulw<INV> (val, wp[k2]);
+#else
         if (k2 > 0) val = cmulw<INV> (val, tw2[(k2 - 1) * 16 + n3]);
+#endif
         row[k2 * 17] = val;
     }
 }
