@@ -26,11 +26,17 @@
                             //    1.7 % faster); 0: product of two small shared-memory factors (two loads and a complex multiply)
 #endif
 
-// EXPERIMENT (FX_TW_POWERS=1): only the twiddles W^1, W^2, W^4, W^8 of a thread are loaded (exact table values); the other
-// eleven are products of those, at most three multiplications deep (W^15 = W^8 W^4 W^2 W^1): 11 packed complex multiplies in
-// place of 11 loads per stage and transform.  The loads ride the L1 / shared-memory data pipe, the busiest unit of the kernel.
-#ifndef FX_TW_POWERS
-#define FX_TW_POWERS 0
+// Twiddle powers: only the twiddles W^1, W^2, W^4, W^8 of a thread are loaded (exact table values); the other eleven are
+// products of those, at most three multiplications deep (W^15 = W^8 W^4 W^2 W^1): 11 packed complex multiplies in place of 11
+// loads per stage and transform.  The loads ride the L1 / shared-memory data pipe, the busiest unit of the kernel, and the
+// stage-1 ones (global table through L1) expose their latency.  Measured (profiles/r02_v22_ab_*.txt), kernel ms at
+// N = 4096 / 2048 / 1024:  all loads 68.43 / 33.11 / 34.11;  stage 1 by powers 66.16 / 32.78 / 34.11;  stage 2 by powers
+// 68.14 / 33.51 / 34.23;  both 65.84 / 33.25 / 33.84.  Default: stage 1 always, stage 2 only at N = 4096 (FX_TW2_POWERS 2 = auto).
+#ifndef FX_TW1_POWERS
+#define FX_TW1_POWERS 1                 // stage 1 (twiddles from the global table through L1)
+#endif
+#ifndef FX_TW2_POWERS
+#define FX_TW2_POWERS 2                 // stage 2 (twiddles from shared memory): 0 never, 1 always, 2 for R1 == 16 only
 #endif
 
 namespace fx {
@@ -216,7 +222,7 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
 #if ! FX_TW1_GLOBAL
         const int mh = m >> 4, ml = 16 + (m & 15);
 #endif
-#if FX_TW_POWERS
+#if FX_TW1_POWERS
         float2 wp[16];
         wp[1] = __ldg (&tw1f[m]); wp[2] = __ldg (&tw1f[256 + m]);
         if (R1 > 4) wp[4] = __ldg (&tw1f[3 * 256 + m]);
@@ -230,7 +236,7 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
             float2 val = v[q * R1 + s];
             if (k1 > 0)
             {
-#if FX_TW_POWERS
+#if FX_TW1_POWERS
                 const float2 w = wp[k1];
 #elif FX_TW1_GLOBAL
                 const float2 w = __ldg (&tw1f[(k1 - 1) * 256 + m]);
@@ -256,21 +262,19 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
     butterfly<16, INV> (v);
-#if FX_TW_POWERS
+    constexpr bool kPowers = FX_TW2_POWERS == 1 || (FX_TW2_POWERS == 2 && R1 == 16);
     float2 wp[16];
-    wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[3 * 16 + n3]; wp[8] = tw2[7 * 16 + n3];
-    twiddle_powers<16> (wp);
-#endif
+    if (kPowers)
+    {
+        wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[3 * 16 + n3]; wp[8] = tw2[7 * 16 + n3];
+        twiddle_powers<16> (wp);
+    }
     #pragma unroll
     for (int s = 0; s < 16; ++s)
     {
         const int k2 = out_index<16> (s);
         float2 val = v[s];
-#if FX_TW_POWERS
-        if (k2 > 0) val = cmulw<INV> (val, wp[k2]);
-#else
-        if (k2 > 0) val = cmulw<INV> (val, tw2[(k2 - 1) * 16 + n3]);
-#endif
+        if (k2 > 0) val = cmulw<INV> (val, kPowers ? wp[k2] : tw2[(k2 - 1) * 16 + n3]);
         row[k2 * 17] = val;
     }
 }
