@@ -109,6 +109,10 @@ fx_status   fx_reset (fx_engine* e);
  * RealTimeAnalyser.h:76), [n_tracks][frames][12] smoothed (AudioFeatures::getValue, :84-88, after both
  * analyser bodies of the hop) and [n_tracks][frames][FX_NUM_DIAG]; any may be NULL.
  *
+ * Only complete hops are analysed: n_samples % hop trailing samples are not carried over (pass them again at the head of
+ * the next call).  The offline calls are refused while the real-time workers run, and need the track groups in step
+ * (they are unless the real-time path advanced them independently; fx_reset brings them back).
+ *
  * fx_analyse_host: HOST pointers (pinned or pageable); host<->device copies are inside the call,
  *                  pipelined over track groups; returns when the results are in host memory.
  * fx_analyse_device: DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = the engine's own). */
@@ -183,6 +187,8 @@ fx_status   fx_rt_stop       (fx_engine* e);
 /* Called on a worker thread after the features of `n_new` hops of tracks [first_track, first_track + n_tracks) were
  * published (frame_index = hops analysed so far in that group) -- where RealTimeSpectralAnalyser::run fires its
  * onsetDetectedCallback (RealTimeAnalyser.h:228-229).  Set it before fx_rt_start. */
+/* The callback may read (fx_poll_*, fx_osc_encode_tracks, fx_rt_get_stats); it must not call the parameter, start / stop or
+ * analysis entry points (they wait for the workers). */
 typedef void (*fx_features_callback) (void* user, int first_track, int n_tracks, uint64_t frame_index, int n_new);
 fx_status   fx_set_features_callback (fx_engine* e, fx_features_callback cb, void* user);
 /* A track is what one AnalyserTrackController owns (AnalyserTrackController.h:17-45).  Only active tracks gate their

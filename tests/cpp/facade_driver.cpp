@@ -73,9 +73,31 @@ int main (int argc, char** argv)
         }
     }
     fclose (out);
+    // MainComponent destroys and re-creates controllers as channels toggle (MainComponent.cpp:137-171): the new controller of
+    // channel 0 starts from empty histories while the other channels carry on
+    usleep (100000);                                             // the callbacks of the last hop run right after it was published
+    const int onsetsOfTheRun = onsetCallbacks.load();
+    uint64_t recreatedHops = 0, othersHops = 0;
+    if (T > 1)
+    {
+        tracks[0].reset();
+        tracks[0].reset (new AnalyserTrackController (deviceManager, 0, "Input 0 again", osc, osc, "/Audio/A0"));
+        tracks[0]->prepareToPlay (setup.bufferSize, setup.sampleRate);
+        const long extraHops = 3;
+        for (long pos = 0; pos + block <= extraHops * hopSize; pos += block)
+        {
+            for (int ch = 0; ch < T; ++ch) chans[(size_t) ch] = audio.data() + (size_t) ch * (size_t) S + pos;
+            deviceManager.processBlock (chans.data(), T, block);
+        }
+        deviceManager.waitForHop (0, (uint64_t) extraHops);
+        deviceManager.waitForHop (1, lastHop + (uint64_t) extraHops);
+        float v[FX_NUM_FEATURES];
+        tracks[0]->getFeatures().snapshot (v, &recreatedHops);
+        tracks[1]->getFeatures().snapshot (v, &othersHops);
+    }
     const std::vector<uint8_t> msg = tracks[0]->getOSCSender().encode();
     for (auto& t : tracks) t->stopAnalysis();
-    printf ("hops %llu onset_callbacks %d osc_bytes %zu push_errors %ld\n", (unsigned long long) lastHop, onsetCallbacks.load(), msg.size(),
-            deviceManager.getPushErrorCount());
+    printf ("hops %llu onset_callbacks %d osc_bytes %zu push_errors %ld recreated_hops %llu others_hops %llu\n", (unsigned long long) lastHop,
+            onsetsOfTheRun, msg.size(), deviceManager.getPushErrorCount(), (unsigned long long) recreatedHops, (unsigned long long) othersHops);
     return 0;
 }

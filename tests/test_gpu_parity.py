@@ -357,6 +357,7 @@ def test_cpp_facade_matches_reference_wiring(fx, oracle, tmp_path):
                          check=True, capture_output=True, text=True).stdout
     rows = np.frombuffer((tmp_path / "out.f32").read_bytes(), np.float32).reshape(-1, T, 13)
     assert rows.shape[0] == 80 and "hops 80" in out
+    assert "push_errors 0" in out and "recreated_hops 3 others_hops 83" in out      # a re-created controller starts afresh, its neighbours carry on
     assert np.array_equal(rows[:, 0, 0], np.arange(1, 81, dtype=np.float32))
     o = oracle.analyse(audio, window=N, hop=H, sample_rate=sr, mode=0)
     g = {"raw": None, "smooth": np.ascontiguousarray(rows[:, :, 1:].transpose(1, 0, 2)), "diag": None}
