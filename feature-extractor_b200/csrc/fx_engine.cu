@@ -906,10 +906,10 @@ fx_status analyse_host_pipeline (fx_engine* e, const unsigned char* src, long ro
     const long row_bytes = used * frame_bytes;                        // source bytes per track that cross PCIe
     const bool shared_row = format != 0 && row_stride_bytes == 0;     // every track reads the same interleaved stream
 
-    // Track groups: about thirty per call (the first group's upload and the last group's analysis are the only parts of
+    // Track groups: about fifty per call (the first group's upload and the last group's analysis are the only parts of
     // the pipeline that do not overlap), but never below ~64 MiB of fp32 audio -- small groups would have to cut every
     // track into short chunks to fill the GPU, and each chunk start refills a whole window
-    long want_groups = 32;
+    long want_groups = 48;
     if (const char* env = getenv ("FXB200_PIPE_GROUPS")) { const long v = atol (env); if (v > 0) want_groups = v; }
     long per = (T + want_groups - 1) / want_groups;
     const long per_min = (64L << 20) / (used * (long) sizeof (float));
