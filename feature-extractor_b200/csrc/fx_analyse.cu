@@ -288,8 +288,19 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
 
 // MG: also compute the decision margins (diagnostics, FX_DIAG_*_MARGIN).  They feed nothing: a call that does not ask for the
 // diagnostics runs the instantiation without them -- same features, bit for bit (tests/test_gpu_parity.py).
+// Resident CTAs per SM the kernel is compiled for (register budget = 65536 / (threads x CTAs)): 3 x 256 threads at 80 registers
+// (N = 4096: a fourth CTA would need 64 registers AND 8 KB less shared memory); 7 x 128 and 13 x 64 threads at 72 registers
+// (N = 2048 / 1024: 28 / 26 warps per SM instead of 24; the seventh / thirteenth CTA fits the shared memory only with the compact
+// stage-2 twiddle table, 512 B instead of 1920 B).  Measured against 6 / 12 CTAs at 80 registers: 32.45 vs 32.78 ms at N = 2048,
+// 33.82 vs 33.98 ms at N = 1024 (profiles/r02_v23_ab_occupancy.txt).
+#ifndef FX_CTAS_R8
+#define FX_CTAS_R8 7
+#endif
+#ifndef FX_CTAS_R4
+#define FX_CTAS_R4 13
+#endif
 template <int R1, bool MG>
-__global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 3 : (R1 == 8 ? 6 : 12)))
+__global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 3 : (R1 == 8 ? FX_CTAS_R8 : FX_CTAS_R4)))
 k_analyse (const AnalyseParams p)
 {
     using D = FftDims<R1>;
@@ -323,7 +334,8 @@ k_analyse (const AnalyseParams p)
     const float* tail = p.tail_in + track * (long) (N - H);
 
     if (! FX_TW1_GLOBAL) for (int i = t; i < D::TW1_LEN; i += T) sm.tw1[i] = p.tw1[i];
-    for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[i];
+    if (D::TW2_POWERS) { for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[((1 << (i >> 4)) - 1) * 16 + (i & 15)]; }      // rows k2 = 1, 2, 4, 8
+    else               { for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[i]; }
     if (t == 0) { mbar_init (&sm.mbar, 1); sm.tw1f = p.tw1f; }
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -1394,6 +1406,11 @@ template <int R1> static cudaError_t configure_t()
     cudaError_t ce = cudaFuncSetAttribute (k_analyse<R1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
     if (ce != cudaSuccess) return ce;
     return cudaFuncSetAttribute (k_analyse<R1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
+}
+
+int analyse_ctas_per_sm (int window)
+{
+    return window == 4096 ? 3 : (window == 2048 ? FX_CTAS_R8 : FX_CTAS_R4);
 }
 
 size_t analyse_smem_bytes (int window)

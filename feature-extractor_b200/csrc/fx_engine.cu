@@ -625,7 +625,7 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
 
     fx_engine* e = new fx_engine();
     e->cfg = *cfg; e->N = N; e->H = H; e->M = N / 2; e->NB = N / H; e->log2_hop = ilog2 (H);
-    e->ctas_per_sm = (N == 4096) ? 3 : (N == 2048 ? 6 : 12);
+    e->ctas_per_sm = analyse_ctas_per_sm (N);
     const size_t T = (size_t) cfg->n_tracks;
 
 #define FX_CREATE(call) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) { set_error (nullptr, #call, ce_); free_engine (e); return FX_ERR_CUDA; } } while (0)

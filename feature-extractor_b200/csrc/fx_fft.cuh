@@ -31,13 +31,13 @@
 // loads per stage and transform.  The loads ride the L1 / shared-memory data pipe, the busiest unit of the kernel, and the
 // stage-1 ones (global table through L1) expose their latency.  Measured (profiles/r02_v22_ab_*.txt), kernel ms at
 // N = 4096 / 2048 / 1024:  all loads 68.43 / 33.11 / 34.11;  stage 1 by powers 66.16 / 32.78 / 34.11;  stage 2 by powers
-// 68.14 / 33.51 / 34.23;  both 65.84 / 33.25 / 33.84.  Default: stage 1 always, stage 2 only at N = 4096 (FX_TW2_POWERS 2 = auto).
+// 68.14 / 33.51 / 34.23;  both 65.84 / 33.25 / 33.84.  Default: both stages at every size (see FX_TW2_POWERS below for N = 2048 / 1024).
 #ifndef FX_TW1_POWERS
 #define FX_TW1_POWERS 1                 // stage 1 (twiddles from the global table through L1)
 #endif
 #ifndef FX_TW2_POWERS
-#define FX_TW2_POWERS 2                 // stage 2 (twiddles from shared memory): 0 never, 1 always, 2 for R1 == 16 only
-#endif
+#define FX_TW2_POWERS 1                 // stage 2 (twiddles from shared memory): 0 never, 1 always, 2 for R1 == 16 only.  At N = 2048 /
+#endif                                  // 1024 it costs ~1 % by itself and buys the shared memory for one more resident CTA (fx_analyse.cu)
 
 namespace fx {
 
@@ -205,7 +205,10 @@ template <int R1> struct FftDims
     static constexpr int EX_LEN  = R1 * ROW;           // float2 elements in the exchange buffer
     static constexpr int TW1_LEN = (R1 - 1) * 32;      // float2, tw1[(k1 - 1) * 32 + mh]      = W_N^(16 mh k1)   (mh < 16)
                                                        //         tw1[(k1 - 1) * 32 + 16 + ml] = W_N^(ml k1)      (ml < 16)
-    static constexpr int TW2_LEN = 15 * 16;            // float2, tw2[(k2 - 1) * 16 + n3]      = W_256^(n3 k2)
+    static constexpr int TW2_FULL = 15 * 16;           // float2, tw2[(k2 - 1) * 16 + n3]      = W_256^(n3 k2)
+    // stage-2 twiddles by powers: the shared-memory copy holds only the rows k2 = 1, 2, 4, 8 (in that order)
+    static constexpr bool TW2_POWERS = FX_TW2_POWERS == 1 || (FX_TW2_POWERS == 2 && R1 == 16);
+    static constexpr int TW2_LEN = TW2_POWERS ? 4 * 16 : TW2_FULL;
 };
 
 // Stage 1 on v (slot q * R1 + n1 = input n1 of butterfly q), then twiddle and store to ex.
@@ -252,7 +255,7 @@ __device__ __forceinline__ void fft_stage1_store (float2* v, int m0, float2* __r
 }
 
 // Stage 2 in place (one 16-point butterfly per thread).  Caller syncs before and after.
-template <int R1, bool INV>
+template <int R1, bool INV, bool POWERS = FftDims<R1>::TW2_POWERS>
 __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, const float2* __restrict__ tw2)
 {
     using D = FftDims<R1>;
@@ -262,11 +265,11 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = row[n2 * 17];
     butterfly<16, INV> (v);
-    constexpr bool kPowers = FX_TW2_POWERS == 1 || (FX_TW2_POWERS == 2 && R1 == 16);
+    constexpr bool kPowers = POWERS;                      // the table is then the compact one: rows k2 = 1, 2, 4, 8
     float2 wp[16];
     if (kPowers)
     {
-        wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[3 * 16 + n3]; wp[8] = tw2[7 * 16 + n3];
+        wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[2 * 16 + n3]; wp[8] = tw2[3 * 16 + n3];
         twiddle_powers<16> (wp);
     }
     #pragma unroll

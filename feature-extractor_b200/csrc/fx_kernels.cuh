@@ -59,6 +59,7 @@ struct AnalyseParams
     int*         first_idx;        // [n_tracks][n_chunks]     frame index of the first non-silent frame, -1 if none
 };
 
+int         analyse_ctas_per_sm (int window);      // resident CTAs per SM k_analyse is compiled for (chunk heuristic)
 cudaError_t launch_analyse (int window, long n_tracks, const AnalyseParams& p, cudaStream_t stream);
 cudaError_t configure_analyse (int window);             // opt in to the dynamic shared memory the kernel needs
 size_t      analyse_smem_bytes (int window);

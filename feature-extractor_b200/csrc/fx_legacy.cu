@@ -81,13 +81,13 @@ __global__ void __launch_bounds__ (16 * R1) k_legacy_spectrum (const LegacyParam
     using D = FftDims<R1>;
     constexpr int N = D::N, T = D::T, Q1 = D::Q1;
     __shared__ float2 ex[D::EX_LEN];
-    __shared__ float2 tw2[D::TW2_LEN];
+    __shared__ float2 tw2[D::TW2_FULL];
     __shared__ double red[8];
     const int t = threadIdx.x;
     const long row = blockIdx.x;
     const long track = row / p.n_frames;
     const int frame = (int) (row % p.n_frames);
-    for (int i = t; i < D::TW2_LEN; i += T) tw2[i] = p.tw2[i];
+    for (int i = t; i < D::TW2_FULL; i += T) tw2[i] = p.tw2[i];
     const float* src = p.audio + track * p.track_stride;
     // :150-161: the window is centred on sample frame * stepSize unless the whole signal is one frame
     const long origin = p.n_frames == 1 ? 0 : (long) frame * p.step - N / 2;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__ (16 * R1) k_legacy_spectrum (const LegacyParam
     __syncthreads();
     fft_stage1_store<R1, false> (v, t, ex, nullptr, p.tw1f);
     __syncthreads();
-    fft_stage2<R1, false> (t, ex, tw2);
+    fft_stage2<R1, false, false> (t, ex, tw2);
     __syncwarp();
     fft_stage3<R1, false> (t, ex);
     __syncthreads();
