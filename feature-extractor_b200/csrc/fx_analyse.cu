@@ -232,15 +232,13 @@ template <int R1> struct Smem
     alignas (128) float ring[N];     // ring[a & (N-1)] = absolute sample a of the track (bulk-copy destination, float4 reads)
     alignas (16) float pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
     double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
-    int      icount[NW];             // flatness gate count, warp totals
-    int      ipeaks[NW];             // number of spectral peaks, warp totals
     double   scan_m[NW];             // flatness product scan, warp totals
     int      scan_e[NW];
     double   pscan[NW];              // pitch cumulative sum scan, warp totals
     unsigned ubest[NW];             // smallest cnd of the lag search range, warp minima (bit patterns)
     unsigned ugidx[NW];             // first index holding it (only formed when no lag crosses the threshold)
     unsigned ucodes[2][NW];
-    float    fmins[3][NW];           // [0] flatness gate margin, [1] max |Re|, |Im| of the lower bins (slope quirk), [2] peak margin
+    float    fmins[3][NW];           // [0] flatness gate margin, [2] peak margin (diagnostics)
     float    fmaxs[NW];
     float    psums[NW];
     float    pmins[2][NW];           // pitch margin / runner-up partials
@@ -325,10 +323,6 @@ k_analyse (const AnalyseParams p)
     }
 
     const int H = p.hop, NB = N >> p.log2_hop;
-#if ! FX_SINGLE_PASS
-    const double nyquist = p.sample_rate / 2.0;
-    const double frpb = nyquist / (double) M;
-#endif
     const float gain = p.gain[track];
     const float* src = p.audio + track * p.track_stride;
     const float* tail = p.tail_in + track * (long) (N - H);
@@ -396,7 +390,9 @@ k_analyse (const AnalyseParams p)
     {
         const long j_new = p.first_hop + f;
         const long a0 = (j_new - (NB - 1)) * (long) H;              // absolute sample index of window sample 0
-        FrameRec* rec = p.rec + (track * p.n_frames + f);
+        unsigned char* rec_bytes = p.rec + (size_t) (track * p.n_frames + f) * frame_rec_bytes (N);
+        FrameHead* rec = reinterpret_cast<FrameHead*> (rec_bytes);
+        WarpPart* rec_w = reinterpret_cast<WarpPart*> (rec_bytes + sizeof (FrameHead));           // [NW]
 
         mbar_wait (&sm.mbar, phase);
         phase ^= 1u;
@@ -544,14 +540,11 @@ k_analyse (const AnalyseParams p)
 
         // =========================== spectral features, pass 1 ========================================
         ME lprod = me_one();
-        double flat_sum_thread = 0.0;
         {
             const float pr[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
             double mag_sum = 0.0, weighted = 0.0, flux = 0.0, lhr = 0.0, flat_sum = 0.0;
-#if FX_SINGLE_PASS
             double s2 = 0.0, s4 = 0.0;
             const double x0 = ((double) b0 + 0.5) * inv_m;                                        // (bin + 1/2) / M, exact
-#endif
             int count = 0;
             float maxre = 0.0f;
             // gate margin: the smallest distance of |Re| from sqrt (eps), relative to sqrt (eps) -- a lower bound of the
@@ -581,28 +574,16 @@ k_analyse (const AnalyseParams p)
                     esum += q.e;
                 }
                 if (MG) gate_d = fminf (gate_d, fabsf (fabsf (cr[j]) - gate_s));
-#if FX_SINGLE_PASS
                 const double x = x0 + (double) j * inv_m;                                        // fc / nyquist (:70, :137)
                 const double xm = x * mg;
                 weighted += xm;
                 s2 = fma (x, xm, s2);
                 s4 = fma (mg, mg, s4);
-#else
-                const double fc = (double) bin * frpb + (frpb / 2.0);                            // :70
-                weighted += fc * mg;
-#endif
                 maxre = fmaxf (maxre, fabsf (cr[j]));
             }
             lprod = me_from (mprod); lprod.e += esum;
-#if FX_SINGLE_PASS
             double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, 0.0 };
             warp_sum_t<8> (s8, lane);
-            (void) flat_sum_thread;
-#else
-            double s4[4] = { mag_sum, weighted, flux, lhr };
-            warp_sum_t<4> (s4, lane);
-            flat_sum_thread = flat_sum;                                                           // summed with the pass-2 values
-#endif
             const int wcount = warp_addi (count);
             const float wmax = warp_max_nonneg (maxre);
             const float wraw = warp_max_nonneg (rawmax);
@@ -620,30 +601,28 @@ k_analyse (const AnalyseParams p)
             ME exc; exc.m = __shfl_up_sync (0xffffffffu, inc.m, 1); exc.e = __shfl_up_sync (0xffffffffu, inc.e, 1);
             if (lane == 0) exc = me_one();
             lprod = exc;                                                                         // lane-exclusive prefix within the warp
-            if (lane == 31) { sm.scan_m[warp] = inc.m; sm.scan_e[warp] = inc.e; }
-#if FX_SINGLE_PASS
-            if (lane < 8) sm.red[1][warp_sum_slot<8> (lane)][warp] = s8[0];                      // slots 0..6: S0, W1, flux, lhr, S2, S4, flat_sum
-#else
-            if (lane < 4) sm.red[1][warp_sum_slot<4> (lane)][warp] = s4[0];
-#endif
+            // The warp's partials leave for K1b from here (the frame record's WarpPart of this warp, one 64-byte run); only what this CTA's own
+            // threads need -- the magnitude sum, the largest |Re|, the norm of P and the product's warp totals -- also goes
+            // through shared memory.  After the transposed butterfly lane l < 8 holds the warp total of value warp_sum_slot<8> (l):
+            // 0 S0, 1 W1, 2 flux, 3 lhr, 4 S2, 5 S4, 6 flat_sum (7: zero).
+            WarpPart* wp = &rec_w[warp];
+            if (lane == 31) { sm.scan_m[warp] = inc.m; sm.scan_e[warp] = inc.e; wp->scan_m = inc.m; wp->scan_e = inc.e; }
+            if (lane < 8) wp->p1[warp_sum_slot<8> (lane)] = s8[0];
+            if (lane == 0) sm.red[1][0][warp] = s8[0];                                            // S0: every thread needs the magnitude sum
             if (lane == 0)
             {
-                sm.icount[warp] = wcount;
+                wp->count = wcount; wp->rawmax = wraw;
                 sm.fmaxs[warp] = wmax;
                 if (MG) sm.fmins[0][warp] = wmar;
-                sm.fmins[1][warp] = wraw;
                 sm.psums[warp] = wps;
             }
         }
         __syncthreads();
-        // every thread needs the magnitude sum, the centroid and the maxima; flux, the low-energy sum, the flatness sums
-        // and the gate margin only go into the record and are combined by thread 0 when it writes it
         double mag_sum = 0.0;
         float maxre_all = 0.0f, psum_all = 0.0f;
         ME prefix = me_one();
-#if FX_SINGLE_PASS
         // every thread needs the magnitude sum (silence gate), the largest |Re| (exponent budget below) and the norm of P;
-        // everything else of the pass only goes into the record and is combined by the record stage
+        // everything else of the pass has already left for K1b as per-warp partials
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
@@ -651,28 +630,11 @@ k_analyse (const AnalyseParams p)
             maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
             psum_all += sm.psums[w];
         }
-#else
-        double weighted = 0.0;
-        float rawmax_all = 0.0f;
-        #pragma unroll
-        for (int w = 0; w < NW; ++w)
-        {
-            mag_sum += sm.red[1][0][w]; weighted += sm.red[1][1][w];
-            maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
-            rawmax_all = fmaxf (rawmax_all, sm.fmins[1][w]);
-            psum_all += sm.psums[w];
-        }
-#endif
         #pragma unroll 1
         for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
         const double maxmag = (double) maxre_all * (double) maxre_all;
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
-#if ! FX_SINGLE_PASS
-        const float centroid = (float) (weighted / mag_sum);                                      // :127
-        const double max_e = fmax ((double) rawmax_all, maxmag);                                  // :153-163
-        const double inv_max_e = 1.0 / max_e;
-#endif
         // how far 8 gated bins can move the exponent of the running flatness product: every gated magnitude lies in
         // (eps, maxmag], so its exponent is bounded by the larger of the two ends' (CTA-uniform, no per-bin bookkeeping)
         int e_budget = 0;
@@ -683,30 +645,8 @@ k_analyse (const AnalyseParams p)
             e_budget = 8 * (max (abs (e_hi), abs (e_lo)) + 2);
         }
 
-        // =========================== pass 2: spread, slope sums, energy variance, flatness range events ===
-        // :177 meanE = (sum of mag / maxE) / M.  The reference's third pass (:182-190, deviations from meanE) runs inside
-        // this one because the mean follows from pass 1's magnitude sum: sum (mag * (1 / maxE)) and magSum * (1 / maxE)
-        // differ by fp64 rounding only (1e-16 relative on a feature compared at 1e-4).
-#if ! FX_SINGLE_PASS
-        const double mean_e = (mag_sum * inv_max_e) * inv_m;
-#endif
+        // =========================== flatness range events ==============================================
         {
-#if ! FX_SINGLE_PASS
-            double var = 0.0, sie = 0.0, evar = 0.0;
-            const double cn = (double) centroid / nyquist;                                        // :137
-            #pragma unroll
-            for (int j = 0; j < 8; ++j)
-            {
-                const int bin = b0 + j;
-                const double mg = (double) cr[j] * (double) cr[j];
-                const double dv = ((double) bin + 0.5) * inv_m - cn;                              // fc / nyquist = (bin + 1/2) / M
-                var += (dv * dv) * mg;
-                const double e = mg * inv_max_e;                                                  // :172
-                sie += (double) bin * e;                                                          // :175
-                const double de = e - mean_e;                                                     // :182-190
-                evar += de * de;
-            }
-#endif
             // The running product can leave the normal fp64 range inside this thread's bins only if its prefix is still in
             // range and the exponent budget of its bins reaches a limit.  Such a thread runs the reference's own sequential IEEE
             // multiply (:92) over its 8 bins, from registers, starting at its prefix (which equals the reference's running
@@ -733,11 +673,6 @@ k_analyse (const AnalyseParams p)
                 }
                 if (left) { ev_code = (unsigned) t; ev_prod = prod; }
             }
-#if ! FX_SINGLE_PASS
-            double s4[4] = { var, sie, flat_sum_thread, evar };
-            warp_sum_t<4> (s4, lane);
-            if (lane < 4) sm.red[0][1 + warp_sum_slot<4> (lane)][warp] = s4[0];                   // slots 1..4: var, sie, flat_sum, evar
-#endif
             const unsigned wev = warp_minu (ev_code);
             if (lane == 0) sm.ucodes[0][warp] = wev;
             if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // the warp's earliest event thread
@@ -745,12 +680,7 @@ k_analyse (const AnalyseParams p)
         if (t == 0)
         {
             // the part of the spectral record every thread already holds (the reductions follow after the next transform)
-#if FX_SINGLE_PASS
-            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->have_prev = have_prev ? 1.0f : 0.0f;
-#else
-            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->weighted = weighted; rec->mean_e = mean_e; rec->max_e = max_e;
-            rec->centroid = centroid; rec->have_prev = have_prev ? 1.0f : 0.0f;
-#endif
+            rec->rms_sum = rms_sum; rec->mag_sum = mag_sum; rec->maxmag = maxmag; rec->have_prev = have_prev ? 1.0f : 0.0f;
         }
         if (! silent)
         {
@@ -1119,24 +1049,16 @@ k_analyse (const AnalyseParams p)
             double s1[1] = { inharm };
             warp_sum<1> (s1);
             const int wnp = warp_addi (npeaks);
-            if (lane == 0) sm.red[1][7][warp] = s1[0];                                            // slot 7: inharmonicity sum
-            if (lane == 0) sm.ipeaks[warp] = wnp;
+            if (lane == 0) { rec_w[warp].inharm = s1[0]; rec_w[warp].npeaks = wnp; }           // K1b sums the warps' parts
             if (MG) { const float wpk = warp_min_nonneg (pkm); if (lane == 0) sm.fmins[2][warp] = wpk; }
         }
         __syncthreads();
-        // ---- the frame's record (what K1b needs), one part per warp ---------------------------------------------------
-        // No barrier closes the frame.  Every per-warp partial of the frame is still in its slot (each reduction of a frame has
-        // its own slot, and none is written again before the barriers inside the next frame's first transform, which need
-        // every warp).  Lane w < NW of a warp loads warp w's partial, a butterfly over those lanes sums them, and the warp
-        // stores its fields; the five parts run on different warps, so no single warp is late for the next frame's barrier.
+        // ---- what is left of the frame's record ----------------------------------------------------------------------
+        // The sums only K1b looks at left as per-warp partials where they were formed (the record's WarpParts); what remains here are the
+        // values every thread holds (lag, harmonic sum and maximum), the 18 harmonic-energy maxima, the margins (MG) and the
+        // flatness product's range event, each on its own warp.  No barrier closes the frame: what these parts read (the
+        // P / Re A array, per-warp slots of earlier phases) is not written again before the next frame's pass 1.
         {
-            constexpr int LOG_NW = NW == 8 ? 3 : (NW == 4 ? 2 : 1);
-            auto sum_nw = [&] (double v) -> double                  // sum over lanes 0 .. NW-1 (all lanes must call)
-            {
-                #pragma unroll
-                for (int sft = 0; sft < LOG_NW; ++sft) v += __shfl_xor_sync (0xffffffffu, v, 1 << sft);
-                return v;
-            };
             const bool ld = lane < NW;
             if (warp == 0 % NW)
             {
@@ -1160,8 +1082,6 @@ k_analyse (const AnalyseParams p)
             }
             if (warp == 1 % NW)
             {
-                const double inharm = sum_nw (ld ? sm.red[1][7][lane] : 0.0);
-                const int npeaks = warp_addi (ld ? sm.ipeaks[lane] : 0);
                 float pkm = 1.0f, pmm = 1.0f;
                 if (MG)
                 {
@@ -1172,56 +1092,23 @@ k_analyse (const AnalyseParams p)
                 }
                 if (lane == 0)
                 {
-                    rec->lag = (float) lag_i; rec->pitch_margin = pmm;
-                    rec->hsum = hsum; rec->hmax = hmax; rec->inharm = inharm;                     // K1b divides (:77, :237)
-                    rec->npeaks = hsilent ? 0.0f : (float) npeaks; rec->peak_margin = pkm;
+                    rec->lag = (float) lag_i; rec->pitch_margin = pmm; rec->peak_margin = pkm;
+                    rec->hsum = hsum; rec->hmax = hmax;                                           // K1b divides (:77, :237)
                 }
             }
-            if (warp == 2 % NW)
+            if (MG && warp == 3 % NW)
             {
-                const double flux = sum_nw (ld ? sm.red[1][2][lane] : 0.0), lhr = sum_nw (ld ? sm.red[1][3][lane] : 0.0);
-                const double flat_sum = sum_nw (ld ? sm.red[FX_SINGLE_PASS ? 1 : 0][FX_SINGLE_PASS ? 6 : 3][lane] : 0.0);
-                const int count = warp_addi (ld ? sm.icount[lane] : 0);
-                if (lane == 0) { rec->flux = flux; rec->lhr = lhr; rec->flat_sum = flat_sum; rec->count = (double) count; }
-            }
-            if (warp == 3 % NW)
-            {
-                const float flat_margin = MG ? warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f) : 1.0f;
-#if FX_SINGLE_PASS
-                // the raw moments (K1b forms spread, slope sums and energy variance from them) and the slope's largest value (:153-163)
-                const double w1 = sum_nw (ld ? sm.red[1][1][lane] : 0.0), s2 = sum_nw (ld ? sm.red[1][4][lane] : 0.0);
-                const double s4 = sum_nw (ld ? sm.red[1][5][lane] : 0.0);
-                const float rawmax_all = warp_max_nonneg (ld ? sm.fmins[1][lane] : 0.0f);
-                if (lane == 0)
-                {
-                    rec->weighted = w1; rec->var = s2; rec->evar = s4; rec->flat_margin = flat_margin;
-                    rec->max_e = fmax ((double) rawmax_all, maxmag);
-                }
-#else
-                const double var = sum_nw (ld ? sm.red[0][1][lane] : 0.0), sie = sum_nw (ld ? sm.red[0][2][lane] : 0.0);
-                const double evar = sum_nw (ld ? sm.red[0][4][lane] : 0.0);
-                if (lane == 0) { rec->var = var; rec->sie = sie; rec->evar = evar; rec->flat_margin = flat_margin; }
-#endif
+                const float flat_margin = warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f);
+                if (lane == 0) rec->flat_margin = flat_margin;
             }
             if (warp == 4 % NW)
             {
-                // flatness product: the offer of the earliest event thread, else the product of the warp totals of the scan
+                // flatness product: without a range event K1b multiplies the warps' totals (flat_state -1); else the offer of the
+                // earliest event thread is continued here
                 const unsigned evc = ld ? sm.ucodes[0][lane] : 0xffffffffu;
                 const unsigned ev = warp_minu (evc);
-                double product; float flat_state = 0.0f;
-                if (ev == 0xffffffffu)
-                {
-                    ME tot = me_one();
-                    if (ld) { tot.m = sm.scan_m[lane]; tot.e = sm.scan_e[lane]; }
-                    #pragma unroll
-                    for (int sft = 0; sft < LOG_NW; ++sft)
-                    {
-                        ME o; o.m = __shfl_xor_sync (0xffffffffu, tot.m, 1 << sft); o.e = __shfl_xor_sync (0xffffffffu, tot.e, 1 << sft);
-                        tot = me_mul (tot, o);
-                    }
-                    product = ldexp_normal (tot.m, tot.e);
-                }
-                else
+                double product = 0.0; float flat_state = -1.0f;
+                if (ev != 0xffffffffu)
                 {
                     const int ev_warp = __ffs ((int) __ballot_sync (0xffffffffu, evc == ev)) - 1;
                     product = sm.ev_prod[ev_warp];
@@ -1255,7 +1142,7 @@ k_analyse (const AnalyseParams p)
                     }
                     flat_state = (product == 0.0) ? 1.0f : (isinf (product) ? 2.0f : 0.0f);
                 }
-                if (lane == 0) { rec->product = product; rec->flat_state = silent ? 3.0f : flat_state; }
+                if (lane == 0) { rec->product = product; rec->flat_state = silent ? 3.0f : flat_state; if (! MG) rec->flat_margin = 1.0f; }
             }
         }
     }
@@ -1273,53 +1160,135 @@ k_analyse (const AnalyseParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1b: the scalar tail of both analyser bodies, one thread per frame.
-__global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
+// K1b: the scalar tail of both analyser bodies, one thread per frame, one warp per batch of 32 consecutive frames.
+// A batch's records are one contiguous run of 32 * frame_rec_bytes (10.5 .. 28.5 KB): it arrives in shared memory by ONE
+// bulk copy (a thread reading its own 336 .. 912-byte record straight from global memory touches a different sector with
+// every load).  The tail is a long dependent fp64 chain (pow, five log10, three sqrt), so it needs many resident warps, and
+// the staged records would cap them: a block of 12 warps therefore shares THREE staging buffers in turn.  Warp w waits for
+// its batch in buffer w % 3, reduces the per-warp partials of its 32 frames into registers, hands the buffer to batch
+// w + 3 (it issues that copy itself: no "buffer empty" barrier) and runs the tail while the later batches stream in.
+#ifndef FX_FZ_WARPS
+#define FX_FZ_WARPS 12
+#endif
+#ifndef FX_FZ_BLOCKS
+#define FX_FZ_BLOCKS 2
+#endif
+constexpr int kFzWarps = FX_FZ_WARPS, kFzBufs = 3;
+constexpr int kFinalizeRows = 32 * kFzWarps;
+template <int NW>
+__global__ void __launch_bounds__ (kFinalizeRows, FX_FZ_BLOCKS) k_finalize (const FinalizeParams p)
 {
-    const long idx = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.n_rows) return;
-    const FrameRec r = p.rec[idx];
+    constexpr size_t RB = sizeof (FrameHead) + NW * sizeof (WarpPart);
+    constexpr size_t BB = 32 * RB;
+    extern __shared__ __align__ (128) unsigned char fz_smem[];            // [kFzBufs][BB]
+    __shared__ uint64_t fz_full[kFzWarps];                              // one per batch, each completes once (a waiter may lag one phase at most)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long row0 = (long) blockIdx.x * kFinalizeRows;
+    auto batch_rows = [&] (int batch) -> int
+    {
+        const long left = p.n_rows - (row0 + 32L * batch);
+        return batch < kFzWarps ? (int) (left < 0 ? 0 : (left > 32 ? 32 : left)) : 0;
+    };
+    auto issue = [&] (int batch)                                          // one lane: start the copy of a batch's records
+    {
+        const int rows = batch_rows (batch);
+        if (rows <= 0) return;
+        uint64_t* bar = &fz_full[batch];
+        mbar_expect_tx (bar, (uint32_t) (rows * RB));
+        bulk_g2s (fz_smem + (batch % kFzBufs) * BB, p.rec + (size_t) (row0 + 32L * batch) * RB, (uint32_t) (rows * RB), bar);
+    };
+    if (threadIdx.x == 0)
+    {
+        for (int b = 0; b < kFzWarps; ++b) mbar_init (&fz_full[b], 1);
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp < kFzBufs && lane == 0) issue (warp);
+    const int rows = batch_rows (warp);
+    if (rows <= 0) return;                                                // (whole warp: the later batches are empty as well)
+    mbar_wait (&fz_full[warp], 0u);
+    const unsigned char* mine = fz_smem + (warp % kFzBufs) * BB + (size_t) lane * RB;     // lanes >= rows read stale bytes and leave below
+    const FrameHead r = *reinterpret_cast<const FrameHead*> (mine);
+    const WarpPart* rw = reinterpret_cast<const WarpPart*> (mine + sizeof (FrameHead));
+    const long idx = row0 + 32L * warp + lane;
     float* out = p.raw + idx * FX_NUM_FEATURES;
-    const int N = p.window, M = N / 2;
+    const int N = p.window, M = N / 2;                            // NW = N / 512 warps of the K1 CTA left the partials
     const double nyquist = p.sample_rate / 2.0;
+
+    // ---- the per-warp partials, added over the warps as a pairwise tree (the order of a butterfly over the warps) ------
+    // (value by value, so that at most NW partials are live at a time)
+    auto tree = [&] (auto get) -> double
+    {
+        double v[NW];
+        #pragma unroll
+        for (int w = 0; w < NW; ++w) v[w] = get (w);
+        #pragma unroll
+        for (int half = 1; half < NW; half <<= 1)
+            #pragma unroll
+            for (int w = 0; w < NW; w += 2 * half) v[w] += v[w + half];
+        return v[0];
+    };
+    const double w1 = tree ([&] (int w) { return rw[w].p1[1]; }), flux = tree ([&] (int w) { return rw[w].p1[2]; });
+    const double lhr = tree ([&] (int w) { return rw[w].p1[3]; }), s2 = tree ([&] (int w) { return rw[w].p1[4]; });
+    const double s4 = tree ([&] (int w) { return rw[w].p1[5]; }), flat_sum = tree ([&] (int w) { return rw[w].p1[6]; });
+    const double inharm = tree ([&] (int w) { return rw[w].inharm; });
+    int count_i = 0, npeaks_i = 0;
+    float rawmax = 0.0f;
+    #pragma unroll
+    for (int w = 0; w < NW; ++w) { count_i += rw[w].count; npeaks_i += rw[w].npeaks; rawmax = fmaxf (rawmax, rw[w].rawmax); }
+    ME tot[NW];
+    #pragma unroll
+    for (int w = 0; w < NW; ++w) { tot[w].m = rw[w].scan_m; tot[w].e = rw[w].scan_e; }
+    // every value of the batch is in registers: the buffer goes to batch warp + kFzBufs
+    __syncwarp();
+    if (lane == 0 && batch_rows (warp + kFzBufs) > 0) { fence_proxy_async(); issue (warp + kFzBufs); }
+    if (lane >= rows) return;
+
+    const double count = (double) count_i;
+    const double max_e = fmax ((double) rawmax, r.maxmag);                                        // SpectralCharacteristics.h:153-163
+    // flatness product (:89-94): K1 reports a range event with the replayed product; otherwise the product of the warps' totals
+    double product = r.product; float flat_state = r.flat_state;
+    if (flat_state < 0.0f)
+    {
+        #pragma unroll
+        for (int half = 1; half < NW; half <<= 1)
+            #pragma unroll
+            for (int w = 0; w < NW; w += 2 * half) tot[w] = me_mul (tot[w], tot[w + half]);
+        product = ldexp_normal (tot[0].m, tot[0].e);
+        flat_state = 0.0f;
+    }
 
     // ---- spectral body (SpectralCharacteristics.h:100-143, :145-200) ------------------------------------------
     const float rms = (float) sqrt (r.rms_sum / (double) N);                                      // getRMSLevel
     const float log_rms = (float) log10 ((double) __fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));       // RealTimeAnalyser.h:208
     const double eps = 0.01 * (double) log_rms;                                                   // :108
     const bool silent = ! (r.mag_sum > 0.05);                                                     // :121-123
-#if FX_SINGLE_PASS
-    // K1 leaves raw moments over x = (bin + 1/2) / M = fc / nyquist: weighted = W1 = sum x mag, var = S2 = sum x^2 mag,
-    // evar = S4 = sum mag^2 (see FX_SINGLE_PASS at the top of this file)
-    const double w1 = r.weighted, s2 = r.var, s4 = r.evar;
+    // K1 leaves raw moments over x = (bin + 1/2) / M = fc / nyquist: W1 = sum x mag, S2 = sum x^2 mag, S4 = sum mag^2
+    // (see FX_SINGLE_PASS at the top of this file)
     const float  centroid = (float) ((w1 * nyquist) / r.mag_sum);                                 // :127 weighted / magSum
     const double cn = (double) centroid / nyquist;                                                // :137
     const double var = (s2 - 2.0 * cn * w1) + cn * cn * r.mag_sum;                                // :135-139
-    const double inv_max_e = 1.0 / r.max_e;
+    const double inv_max_e = 1.0 / max_e;
     const double mean_e = (r.mag_sum * inv_max_e) / (double) M;                                   // :177
     const double sie = ((double) M * w1 - 0.5 * r.mag_sum) * inv_max_e;                           // :175 sum i e_i
     double evar = s4 * inv_max_e * inv_max_e - (double) M * mean_e * mean_e;                      // :182-190
     if (evar < 0.0) evar = 0.0;                                   // rounding of the difference (a spectrum flat to ~1e-8)
-#else
-    const float  centroid = r.centroid;
-    const double var = r.var, mean_e = r.mean_e, sie = r.sie, evar = r.evar;
-#endif
-    float gate_margin = fminf (relmargin_d (r.mag_sum, 0.05), relmargin_d (r.max_e, 0.0001));
+    float gate_margin = fminf (relmargin_d (r.mag_sum, 0.05), relmargin_d (max_e, 0.0001));
     float o_centroid = 0.0f, o_spread = 0.0f, o_flat = 0.0f, o_ler = 0.0f, o_flux = 0.0f, o_slope = 0.0f;
     if (! silent)
     {
         const float max_flux = (float) (M * (M + 1)) / 2.0f;                                      // :111
-        const double inv = 1.0 / (r.count > 0.0 ? r.count : 1.0);                                 // :130
-        const float flat = r.flat_sum > eps ? (float) (pow (r.product, inv) / (inv * r.flat_sum)) : 0.0f;     // :57-60
+        const double inv = 1.0 / (count > 0.0 ? count : 1.0);                                 // :130
+        const float flat = flat_sum > eps ? (float) (pow (product, inv) / (inv * flat_sum)) : 0.0f;     // :57-60
         o_flat = (float) log10 ((double) flat * 9.0 + 1.0);                                       // :132
         const float c = __fdiv_rn (centroid, (float) (nyquist / 2.0));                            // :133
         o_centroid = (float) log10 ((double) __fadd_rn (__fmul_rn (c, 9.0f), 1.0f));              // :134
         const float max_spread = (float) (((double) centroid / nyquist) * (1.0 - ((double) centroid / nyquist)));   // :140
         o_spread = (float) ((var / r.mag_sum) / (double) max_spread);                             // :141
-        o_ler = (float) (r.lhr / r.mag_sum);                                                      // :125
-        o_flux = r.have_prev != 0.0f ? (float) (r.flux / (double) max_flux) : 0.0f;               // :112 (K2 fixes the chunk's first non-silent frame)
+        o_ler = (float) (lhr / r.mag_sum);                                                      // :125
+        o_flux = r.have_prev != 0.0f ? (float) (flux / (double) max_flux) : 0.0f;               // :112 (K2 fixes the chunk's first non-silent frame)
     }
-    if (r.max_e > 0.0001)                                                                         // :165-167
+    if (max_e > 0.0001)                                                                         // :165-167
     {
         const double energy_var = evar / (double) M;
         const double bin_std = sqrt (p.bin_var), energy_std = sqrt (energy_var);
@@ -1354,7 +1323,7 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         o_oer = (float) log10 ((double) (float) oer * 9.0 + 1.0);
         // :237 (K1 leaves the sum of f0Proportion * binMagnitude; with no contributing peak the reference's sum stays 0 whatever
         // the magnitude sum is -- NaN input included)
-        o_inh = (float) log10 ((r.inharm != 0.0 ? r.inharm / r.hsum : 0.0) * 9.0 + 1.0);
+        o_inh = (float) log10 ((inharm != 0.0 ? inharm / r.hsum : 0.0) * 9.0 + 1.0);
     }
     gate_margin = fminf (gate_margin, relmargin_d (r.hsum, 0.005));
 
@@ -1372,9 +1341,9 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         dg[FX_DIAG_TRUE_OER] = o_oer;
         dg[FX_DIAG_LAG] = r.lag;
         dg[FX_DIAG_PITCH_MARGIN] = r.pitch_margin;
-        dg[FX_DIAG_NUM_PEAKS] = r.npeaks;
+        dg[FX_DIAG_NUM_PEAKS] = r.hsum < 0.005 ? 0.0f : (float) npeaks_i;                           // HarmonicCharacteristics.h:88
         dg[FX_DIAG_PEAK_MARGIN] = r.peak_margin;
-        dg[FX_DIAG_FLAT_COUNT] = (float) r.count;
+        dg[FX_DIAG_FLAT_COUNT] = (float) count;
         // The gate compares Re^2 with eps; Re carries the absolute rounding noise of an fp32 FFT (here and in the reference's
         // own transform), taken as 1e-6 of the spectrum's rms like the pitch margin's floor.  For every bin the relative gap
         // shrinks by at most 2 e / sqrt (eps) + e^2 / eps (|Re| >= sqrt (eps) above the gate, the gap is relative to eps below).
@@ -1387,7 +1356,7 @@ __global__ void __launch_bounds__ (128) k_finalize (const FinalizeParams p)
         dg[FX_DIAG_FLAT_MARGIN] = fm;
         dg[FX_DIAG_GATE_MARGIN] = gate_margin;
         dg[FX_DIAG_ONSET_MARGIN] = 1.0f;
-        dg[FX_DIAG_FLAT_STATE] = r.flat_state;
+        dg[FX_DIAG_FLAT_STATE] = flat_state;
     }
 }
 
@@ -1404,6 +1373,8 @@ template <int R1> static cudaError_t launch_t (long n_tracks, const AnalyseParam
 template <int R1> static cudaError_t configure_t()
 {
     cudaError_t ce = cudaFuncSetAttribute (k_analyse<R1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
+    if (ce != cudaSuccess) return ce;
+    ce = cudaFuncSetAttribute (k_finalize<R1 / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kFzBufs * 32 * frame_rec_bytes (256 * R1)));
     if (ce != cudaSuccess) return ce;
     return cudaFuncSetAttribute (k_analyse<R1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (Smem<R1>));
 }
@@ -1449,7 +1420,15 @@ cudaError_t launch_analyse (int window, long n_tracks, const AnalyseParams& p, c
 cudaError_t launch_finalize (const FinalizeParams& p, cudaStream_t stream)
 {
     if (p.n_rows <= 0) return cudaSuccess;
-    k_finalize<<<(unsigned) ((p.n_rows + 127) / 128), 128, 0, stream>>> (p);
+    const unsigned grid = (unsigned) ((p.n_rows + kFinalizeRows - 1) / kFinalizeRows);
+    const size_t smem = (size_t) kFzBufs * 32 * frame_rec_bytes (p.window);
+    switch (p.window)
+    {
+        case 1024: k_finalize<2><<<grid, kFinalizeRows, smem, stream>>> (p); break;
+        case 2048: k_finalize<4><<<grid, kFinalizeRows, smem, stream>>> (p); break;
+        case 4096: k_finalize<8><<<grid, kFinalizeRows, smem, stream>>> (p); break;
+        default:   return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

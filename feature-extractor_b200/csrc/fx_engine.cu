@@ -40,7 +40,7 @@ constexpr int    kMaxGroups = 256;                        // fx_push_block keeps
 // the buffers one run of K1 -> K1b -> K2 -> K3 hands from kernel to kernel
 struct fx_scratch
 {
-    fx::FrameRec* rec = nullptr;        // [tracks][frames]
+    unsigned char* rec = nullptr;       // [tracks][frames] records of fx::frame_rec_bytes (window)
     float* first_spec = nullptr;        // [tracks * chunks][M]
     float* last_spec = nullptr;
     int*   first_idx = nullptr;         // [tracks * chunks]
@@ -220,7 +220,7 @@ fx_status ensure_records (fx_engine* e, long frames)
     FX_CUDA (e, cudaDeviceSynchronize());
     cudaFree (e->scratch.rec);
     e->scratch.rec = nullptr; e->rec_capacity = 0;
-    FX_CUDA (e, cudaMalloc (&e->scratch.rec, (size_t) e->cfg.n_tracks * (size_t) frames * sizeof (fx::FrameRec)));
+    FX_CUDA (e, cudaMalloc (&e->scratch.rec, (size_t) e->cfg.n_tracks * (size_t) frames * fx::frame_rec_bytes (e->N)));
     e->rec_capacity = frames;
     return FX_OK;
 }
@@ -322,7 +322,7 @@ fx_scratch offline_scratch (const fx_engine* e, long t0, long frames, int n_chun
 {
     fx_scratch sc;
     const size_t coff = (size_t) t0 * (size_t) n_chunks;
-    sc.rec = e->scratch.rec + (size_t) t0 * (size_t) frames;
+    sc.rec = e->scratch.rec + (size_t) t0 * (size_t) frames * fx::frame_rec_bytes (e->N);
     sc.first_spec = e->scratch.first_spec + coff * e->M;
     sc.last_spec  = e->scratch.last_spec + coff * e->M;
     sc.first_idx  = e->scratch.first_idx + coff;
@@ -711,7 +711,7 @@ fx_status fx_engine_create (const fx_config* cfg, fx_engine** out)
             FX_CREATE (cudaMalloc (&gp->d_stage, rows * H * sizeof (float)));
             FX_CREATE (cudaMalloc (&gp->d_raw, rows * FX_NUM_FEATURES * sizeof (float)));
             FX_CREATE (cudaMalloc (&gp->d_smooth, rows * FX_NUM_FEATURES * sizeof (float)));
-            FX_CREATE (cudaMalloc (&gp->scratch.rec, rows * sizeof (fx::FrameRec)));
+            FX_CREATE (cudaMalloc (&gp->scratch.rec, rows * fx::frame_rec_bytes (e->N)));
             const size_t pairs = (size_t) gp->n * (size_t) gp->max_chunks;
             FX_CREATE (cudaMalloc (&gp->scratch.first_spec, pairs * e->M * sizeof (float)));
             FX_CREATE (cudaMalloc (&gp->scratch.last_spec,  pairs * e->M * sizeof (float)));

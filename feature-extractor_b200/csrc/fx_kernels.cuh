@@ -11,14 +11,33 @@ constexpr int kHistRows   = 32;   // raw feature rows carried between calls (10-
 constexpr int kMaxOnsetHist = 16;
 #define FX_HER_TAB_STRIDE 20       // shorts per lag in AnalyseParams::her_tab
 
-// Per-frame sums K1 leaves for K1b (k_finalize).  fp64 wherever the reference accumulates in double.
-struct FrameRec
+// What K1 leaves for K1b (k_finalize) per frame: a FrameHead followed by one WarpPart per warp of the K1 CTA (window / 512 of
+// them), frame_rec_bytes (window) per frame.  fp64 wherever the reference accumulates in double.
+// The sums that only K1b looks at leave K1 as PER-WARP partials, stored by each warp where it forms them (one 96-byte run per
+// warp): K1 reduces across warps only what its own threads need (magnitude sum, maxima, the lag search), and no warp collects
+// the others' partials on its way into the next frame's first barrier (-2.4 % kernel time at N = 2048 / 1024, where the five
+// parts of the old record stage shared four / two warps).  K1b adds them in the order of the butterfly K1 used to run
+// (pairwise tree over the warps), so the features are the same bits.
+struct alignas (16) WarpPart
 {
-    double rms_sum, mag_sum, weighted, flux, lhr, flat_sum, count, product, var, sie, mean_e, evar, max_e;   // spectral body
-    double hsum, hmax, inharm;                                                                               // harmonic body
-    float  centroid, flat_margin, flat_state, have_prev, lag, pitch_margin, npeaks, peak_margin;
+    double p1[8];       // pass 1, the transposed butterfly's slots: S0 = sum mag, W1 = sum x mag, flux, low-energy sum, S2 = sum x^2 mag,
+                        // S4 = sum mag^2, gated sum, (unused)            (x = (bin + 1/2) / M)
+    double inharm;      // sum of f0Proportion * binMagnitude over the warp's peaks
+    double scan_m;      // extended-range product of the warp's gated magnitudes: mantissa in [0.5, 1) ...
+    int    scan_e;      // ... and exponent
+    int    count;       // gated bins
+    int    npeaks;
+    float  rawmax;      // max |Re|, |Im| of the lower bins (slope quirk)
+};
+struct alignas (16) FrameHead
+{
+    double rms_sum, mag_sum, maxmag, product, hsum, hmax;
+    float  flat_state;             // 3: silent frame, 0 / 1 / 2: product finite / 0 / inf after a range event (K1 replayed it), -1: no event, K1b multiplies the warp products
+    float  have_prev, lag, pitch_margin, peak_margin, flat_margin;
     float  her_mx[18];             // largest |Re A| around the 15 sub-octave and 3 harmonic bins of f0 (HarmonicCharacteristics.h:147-210), < 0: not used
 };
+static_assert (sizeof (WarpPart) == 96 && sizeof (FrameHead) == 144, "K1b reads the warp parts as runs of 12 doubles behind a 144-byte head");
+__host__ __device__ constexpr size_t frame_rec_bytes (int window) { return sizeof (FrameHead) + (size_t) (window / 512) * sizeof (WarpPart); }
 
 // ---- K1: per-(track, chunk) frame walker ------------------------------------------------------------
 struct AnalyseParams
@@ -53,7 +72,7 @@ struct AnalyseParams
     const int*    ex_off;          // [window + 1] offset of a lag's entries in ex_tab
     short        f0bin_pow2[16];   // her_tab[lag][18] for lag = 2^k (the lags whose f0 bin the kernel does not derive by integer division)
     // outputs
-    FrameRec*    rec;              // [n_tracks][n_frames]
+    unsigned char* rec;            // [n_tracks][n_frames] records of frame_rec_bytes (window) each
     float*       first_spec;       // [n_tracks][n_chunks][M]  Re spectrum (windowed path) of the chunk's first non-silent frame
     float*       last_spec;        // [n_tracks][n_chunks][M]  ... of its last non-silent frame
     int*         first_idx;        // [n_tracks][n_chunks]     frame index of the first non-silent frame, -1 if none
@@ -67,7 +86,7 @@ size_t      analyse_smem_bytes (int window);
 // ---- K1b: scalar tail (pow / log10 / sqrt, gates, clamps), one thread per frame --------------------
 struct FinalizeParams
 {
-    const FrameRec* rec;
+    const unsigned char* rec;      // [n_rows] records of frame_rec_bytes (window)
     long         n_rows;           // n_tracks * n_frames
     int          window;
     double       sample_rate;

@@ -6,6 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 nproc >> gpurun_out/smi.txt; lscpu | grep -E "Model name|NUMA|Socket" >> gpurun_out/smi.txt
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 900 python tools/parity_report.py --out gpurun_out/parity.json 2>&1 | tail -6
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
