@@ -224,23 +224,26 @@ template <int R1> struct Smem
 {
     using D = FftDims<R1>;
     static constexpr int N = D::N, M = N / 2, T = D::T, NW = T / 32;
-    static constexpr int kRed = 10;
 
     float2   ex[D::EX_LEN];          // FFT exchange buffer; doubles as two fp32 work arrays (skewed, N*17/16 floats each)
     float2   tw1[FX_TW1_GLOBAL ? 1 : D::TW1_LEN];     // stage-1 twiddle factors (only when they are not read from the global table)
     float2   tw2[D::TW2_LEN];
     alignas (128) float ring[N];     // ring[a & (N-1)] = absolute sample a of the track (bulk-copy destination, float4 reads)
     alignas (16) float pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
-    double   red[2][kRed][NW];       // block-reduction partials, double buffered by phase parity
-    double   scan_m[NW];             // flatness product scan, warp totals
-    int      scan_e[NW];
-    double   pscan[NW];              // pitch cumulative sum scan, warp totals
-    unsigned ubest[NW];             // smallest cnd of the lag search range, warp minima (bit patterns)
-    unsigned ugidx[NW];             // first index holding it (only formed when no lag crosses the threshold)
-    unsigned ucodes[2][NW];
+    // Per-warp partials every thread reads back after a barrier.  What one reader needs of a warp sits in ONE 16-byte slot: a
+    // broadcast LDS.128 per warp instead of one load per value (these reads were ~40 of the 230 LDS per thread and frame).
+    struct alignas (16) P1Slot  { double s0; float maxre; float psum; };      // pass 1: magnitude sum, largest |Re|, sum of P^2
+    struct alignas (16) ScanSlot { double m; int e; int pad; };               // flatness product scan, warp totals
+    struct alignas (16) LagSlot { double hsum; unsigned first_cross; unsigned best; };   // harmonic magnitude sum; first lag under the threshold, smallest cnd (bit pattern)
+    alignas (16) double rms[NW];     // sum of squares of the frame, warp totals
+    P1Slot   p1s[NW];
+    ScanSlot scan[NW];
+    alignas (16) double pscan[NW];   // pitch cumulative sum scan, warp totals
+    LagSlot  lags[NW];
+    alignas (16) float hmaxs[NW];    // largest |Re A|, warp maxima
+    unsigned ugidx[NW];             // first index holding the smallest cnd (only formed when no lag crosses the threshold)
+    unsigned ucodes[NW];            // flatness product: earliest range-event thread of the warp
     float    fmins[3][NW];           // [0] flatness gate margin, [2] peak margin (diagnostics)
-    float    fmaxs[NW];
-    float    psums[NW];
     float    pmins[2][NW];           // pitch margin / runner-up partials
     unsigned short ndm[T];           // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178)
     double   ev_prod[NW];           // flatness product replayed by the warp's earliest range event
@@ -422,7 +425,7 @@ k_analyse (const AnalyseParams p)
             {
                 double r1[1] = { (double) (sq0 + sq1) * ((double) gain * (double) gain) };       // AudioDataCollector.h:88 applies the gain
                 warp_sum<1> (r1);
-                if (lane == 0) sm.red[0][0][warp] = r1[0];
+                if (lane == 0) sm.rms[warp] = r1[0];
             }
             float y = (t == 0) ? __fmul_rn (xs[0], gain) : __fmul_rn (xs[0], c1g);               // y[0] = x[0]
             ys[0] = y;
@@ -532,7 +535,11 @@ k_analyse (const AnalyseParams p)
         // RMS (RealTimeAnalyser.h:207-208)
         double rms_sum = 0.0;
         #pragma unroll
-        for (int w = 0; w < NW; ++w) rms_sum += sm.red[0][0][w];
+        for (int w = 0; w < NW; w += 2)
+        {
+            const double2 r2 = *reinterpret_cast<const double2*> (&sm.rms[w]);
+            rms_sum += r2.x; rms_sum += r2.y;
+        }
         // K1b recomputes both in double for the RMS feature; here they only set the flatness gate, whose margin is reported
         const float rms = __fsqrt_rn ((float) (rms_sum * (1.0 / (double) N)));
         const float log_rms = log10f (__fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));
@@ -606,15 +613,18 @@ k_analyse (const AnalyseParams p)
             // through shared memory.  After the transposed butterfly lane l < 8 holds the warp total of value warp_sum_slot<8> (l):
             // 0 S0, 1 W1, 2 flux, 3 lhr, 4 S2, 5 S4, 6 flat_sum (7: zero).
             WarpPart* wp = &rec_w[warp];
-            if (lane == 31) { sm.scan_m[warp] = inc.m; sm.scan_e[warp] = inc.e; wp->scan_m = inc.m; wp->scan_e = inc.e; }
+            if (lane == 31)
+            {
+                *reinterpret_cast<double2*> (&sm.scan[warp]) = make_double2 (inc.m, __hiloint2double (0, inc.e));
+                wp->scan_m = inc.m; wp->scan_e = inc.e;
+            }
             if (lane < 8) wp->p1[warp_sum_slot<8> (lane)] = s8[0];
-            if (lane == 0) sm.red[1][0][warp] = s8[0];                                            // S0: every thread needs the magnitude sum
             if (lane == 0)
             {
                 wp->count = wcount; wp->rawmax = wraw;
-                sm.fmaxs[warp] = wmax;
+                // S0: every thread needs the magnitude sum
+                *reinterpret_cast<double2*> (&sm.p1s[warp]) = make_double2 (s8[0], __hiloint2double (__float_as_int (wps), __float_as_int (wmax)));
                 if (MG) sm.fmins[0][warp] = wmar;
-                sm.psums[warp] = wps;
             }
         }
         __syncthreads();
@@ -626,12 +636,13 @@ k_analyse (const AnalyseParams p)
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-            mag_sum += sm.red[1][0][w];
-            maxre_all = fmaxf (maxre_all, sm.fmaxs[w]);
-            psum_all += sm.psums[w];
+            const double2 sl = *reinterpret_cast<const double2*> (&sm.p1s[w]);                    // one LDS.128: { s0, (maxre, psum) }
+            mag_sum += sl.x;
+            maxre_all = fmaxf (maxre_all, __int_as_float (__double2loint (sl.y)));
+            psum_all += __int_as_float (__double2hiint (sl.y));
         }
         #pragma unroll 1
-        for (int w = 0; w < warp; ++w) { ME wt; wt.m = sm.scan_m[w]; wt.e = sm.scan_e[w]; prefix = me_mul (prefix, wt); }
+        for (int w = 0; w < warp; ++w) { const double2 sl = *reinterpret_cast<const double2*> (&sm.scan[w]); ME wt; wt.m = sl.x; wt.e = __double2loint (sl.y); prefix = me_mul (prefix, wt); }
         prefix = me_mul (prefix, lprod);
         const double maxmag = (double) maxre_all * (double) maxre_all;
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
@@ -674,7 +685,7 @@ k_analyse (const AnalyseParams p)
                 if (left) { ev_code = (unsigned) t; ev_prod = prod; }
             }
             const unsigned wev = warp_minu (ev_code);
-            if (lane == 0) sm.ucodes[0][warp] = wev;
+            if (lane == 0) sm.ucodes[warp] = wev;
             if (ev_code != 0xffffffffu && ev_code == wev) sm.ev_prod[warp] = ev_prod;             // the warp's earliest event thread
         }
         if (t == 0)
@@ -733,7 +744,7 @@ k_analyse (const AnalyseParams p)
         float ev_pf = 0.0f;
         if (warp == 4 % NW)
         {
-            const unsigned ev = warp_minu (lane < NW ? sm.ucodes[0][lane] : 0xffffffffu);
+            const unsigned ev = warp_minu (lane < NW ? sm.ucodes[lane] : 0xffffffffu);
             const int b = 8 * ((int) ev + 1) + lane;
             if (ev != 0xffffffffu && ! silent && b < M) ev_pf = prev_g[b];
         }
@@ -797,11 +808,16 @@ k_analyse (const AnalyseParams p)
             if (MG && t == 0) sm.d0 = dv[0];
         }
         __syncthreads();
-        unsigned first_cross = 0xffffffffu, nd_mask = 0u;
+        unsigned first_cross = 0xffffffffu, nd_mask = 0u, wfc, wbest;
         {
             double base = seg_exc;
             #pragma unroll
-            for (int w = 0; w < NW; ++w) if (w < warp) base += sm.pscan[w];
+            for (int w = 0; w < NW; w += 2)
+            {
+                const double2 p2 = *reinterpret_cast<const double2*> (&sm.pscan[w]);
+                if (w < warp) base += p2.x;
+                if (w + 1 < warp) base += p2.y;
+            }
             // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
             float sumf = (float) base;
             float best = 100.0f;
@@ -826,9 +842,8 @@ k_analyse (const AnalyseParams p)
             sm.ndm[t] = (unsigned short) nd_mask;
             if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
             // smallest cnd of the warp (cnd >= 0 orders like its bit pattern)
-            const unsigned wfc = warp_minu (first_cross);
-            const unsigned wbest = warp_minu (__float_as_uint (best));
-            if (lane == 0) { sm.ucodes[1][warp] = wfc; sm.ubest[warp] = wbest; }
+            wfc = warp_minu (first_cross);
+            wbest = warp_minu (__float_as_uint (best));
         }
         // harmonic pass A (independent of the pitch): sum and max of Re A ^2 (HarmonicCharacteristics.h:61-69).  The three
         // neighbours the peak test needs from other threads (bins b0 - 2, b0 - 1, b0 + 8) are fetched now: after the next
@@ -847,7 +862,11 @@ k_analyse (const AnalyseParams p)
             double s1[1] = { hsum };
             warp_sum<1> (s1);
             const float wm = warp_max_nonneg (hmaxre);
-            if (lane == 0) { sm.red[0][5][warp] = s1[0]; sm.fmaxs[warp] = wm; }
+            if (lane == 0)
+            {
+                *reinterpret_cast<double2*> (&sm.lags[warp]) = make_double2 (s1[0], __hiloint2double ((int) wbest, (int) wfc));
+                sm.hmaxs[warp] = wm;
+            }
         }
         __syncthreads();
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
@@ -857,9 +876,24 @@ k_analyse (const AnalyseParams p)
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-            s0 = min (s0, sm.ucodes[1][w]);
-            gbest = min (gbest, sm.ubest[w]);
-            hsum += sm.red[0][5][w]; hmaxre = fmaxf (hmaxre, sm.fmaxs[w]);
+            const double2 sl = *reinterpret_cast<const double2*> (&sm.lags[w]);                   // one LDS.128: { hsum, (first_cross, best) }
+            s0 = min (s0, (unsigned) __double2loint (sl.y));
+            gbest = min (gbest, (unsigned) __double2hiint (sl.y));
+            hsum += sl.x;
+        }
+        if (NW >= 4)
+        {
+            #pragma unroll
+            for (int w = 0; w + 3 < NW; w += 4)
+            {
+                const float4 h4 = *reinterpret_cast<const float4*> (&sm.hmaxs[w]);
+                hmaxre = fmaxf (fmaxf (hmaxre, fmaxf (h4.x, h4.y)), fmaxf (h4.z, h4.w));
+            }
+        }
+        else
+        {
+            const float2 h2 = *reinterpret_cast<const float2*> (&sm.hmaxs[0]);
+            hmaxre = fmaxf (h2.x, h2.y);
         }
         const double hmax = (double) hmaxre * (double) hmaxre;
         const bool crossed = (s0 != 0xffffffffu);
@@ -1105,7 +1139,7 @@ k_analyse (const AnalyseParams p)
             {
                 // flatness product: without a range event K1b multiplies the warps' totals (flat_state -1); else the offer of the
                 // earliest event thread is continued here
-                const unsigned evc = ld ? sm.ucodes[0][lane] : 0xffffffffu;
+                const unsigned evc = ld ? sm.ucodes[lane] : 0xffffffffu;
                 const unsigned ev = warp_minu (evc);
                 double product = 0.0; float flat_state = -1.0f;
                 if (ev != 0xffffffffu)
