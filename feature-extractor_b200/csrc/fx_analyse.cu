@@ -83,6 +83,15 @@ __device__ __forceinline__ void bulk_g2s (void* dst_smem, const void* src_gmem, 
     asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                   :: "r"(smem_u32 (dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS: no register staging) and the arrival of a thread's copies at an mbarrier
+__device__ __forceinline__ void cp_async16 (void* dst_smem, const void* src_gmem)
+{
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32 (dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive (uint64_t* bar)       // arrives (without raising the expected count) once this thread's copies have landed
+{
+    asm volatile ("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32 (bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
@@ -227,9 +236,13 @@ template <int R1> struct Smem
 
     float2   ex[D::EX_LEN];          // FFT exchange buffer; doubles as two fp32 work arrays (skewed, N*17/16 floats each)
     float2   tw1[FX_TW1_GLOBAL ? 1 : D::TW1_LEN];     // stage-1 twiddle factors (only when they are not read from the global table)
-    float2   tw2[D::TW2_LEN];
-    alignas (128) float ring[N];     // ring[a & (N-1)] = absolute sample a of the track (bulk-copy destination, float4 reads)
-    alignas (16) float pa[M + 4];              // P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
+    float2   tw2[D::TW2_POWERS ? 1 : D::TW2_LEN];   // stage-2 twiddle table (by powers: the compact table lives in the holes of the ring instead)
+    // The sample ring and the P / Re A array are SKEWED by one float4 per 32 floats (sk32 below): a thread reads 16 (8)
+    // consecutive floats as float4s, i.e. the lanes of a quarter warp are 64 (32) bytes apart and would share two (four) of the
+    // eight 16-byte bank groups; with the skew every quarter warp covers all eight.  Runs of 32 consecutive floats that start at
+    // a multiple of 32 stay contiguous (the gather of FFT-beta, the 128-byte pieces of the bulk copies).
+    alignas (128) float ring[N + N / 8];       // ring[sk32 (a & (N-1))] = absolute sample a of the track (bulk-copy destination, float4 reads)
+    alignas (16) float pa[M + M / 8 + 4];      // pa[sk32 (k)]: P[k] = Re C[k]^2, k = 0..M (input of FFT-beta), then Re A[k] (harmonic features)
     // Per-warp partials every thread reads back after a barrier.  What one reader needs of a warp sits in ONE 16-byte slot: a
     // broadcast LDS.128 per warp instead of one load per value (these reads were ~40 of the 230 LDS per thread and frame).
     struct alignas (16) P1Slot  { double s0; float maxre; float psum; };      // pass 1: magnitude sum, largest |Re|, sum of P^2
@@ -245,15 +258,21 @@ template <int R1> struct Smem
     unsigned ucodes[NW];            // flatness product: earliest range-event thread of the warp
     float    fmins[3][NW];           // [0] flatness gate margin, [2] peak margin (diagnostics)
     float    pmins[2][NW];           // pitch margin / runner-up partials
-    unsigned short ndm[T];           // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178)
+    union
+    {
+        unsigned short ndm[T];       // per 16-lag segment: bit j set when cnd[j + 1] < cnd[j] does NOT hold (PitchAnalyser.h:178); dead after the lag derivation
+        double   ev_chunk[32];       // 32 gated magnitudes of the product's continuation (record stage, behind the frame's last barrier)
+    };
     double   ev_prod[NW];           // flatness product replayed by the warp's earliest range event
-    double   ev_chunk[32];          // 32 gated magnitudes of the product's continuation (record stage)
     float    d0;                     // autocorrelation at lag 0 (noise floor of the pitch margin)
     uint64_t mbar;
     const float2* tw1f;
 };
 
 extern __shared__ __align__ (128) unsigned char fx_smem_raw[];
+
+// position of element i of an array skewed by one float4 per 32 floats
+__device__ __forceinline__ int sk32 (int i) { return i + ((i >> 5) << 2); }
 
 struct V16 { float2 v[16]; };
 
@@ -267,6 +286,9 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
     Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
     const int t = threadIdx.x;
     fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1, sm.tw1f);
+#if FX_TW2_PREFETCH || FX_STAGE23_SHFL
+    static_assert (! FftDims<R1>::TW2_POWERS, "the experiment paths read the full stage-2 table: build them with -DFX_TW2_POWERS=0");
+#endif
 #if FX_TW2_PREFETCH
     float2 tw[15];
     #pragma unroll
@@ -281,7 +303,7 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
 #if FX_STAGE23_SHFL
     fft_stage23_shfl<R1, false> (t, sm.ex, sm.tw2);         // experiment: the 2 -> 3 exchange by warp shuffles (measured slower)
 #else
-    fft_stage2<R1, false> (t, sm.ex, sm.tw2);
+    fft_stage2<R1, false> (t, sm.ex, FftDims<R1>::TW2_POWERS ? reinterpret_cast<const float2*> (sm.ring + 32) : sm.tw2);
     __syncwarp();                                           // rows are private to a half warp from here on
     fft_stage3<R1, false> (t, sm.ex);
 #endif
@@ -300,6 +322,10 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
 #ifndef FX_CTAS_R4
 #define FX_CTAS_R4 13
 #endif
+// (233 472 bytes of shared memory per SM, 1 KB of it reserved per resident CTA)
+static_assert (3 * (sizeof (Smem<16>) + 1024) <= 233472, "three CTAs of N = 4096 per SM");
+static_assert (FX_CTAS_R8 * (sizeof (Smem<8>) + 1024) <= 233472, "resident CTAs of N = 2048 per SM");
+static_assert (FX_CTAS_R4 * (sizeof (Smem<4>) + 1024) <= 233472, "resident CTAs of N = 1024 per SM");
 template <int R1, bool MG>
 __global__ void __launch_bounds__ (16 * R1, (R1 == 16 ? 3 : (R1 == 8 ? FX_CTAS_R8 : FX_CTAS_R4)))
 k_analyse (const AnalyseParams p)
@@ -331,9 +357,14 @@ k_analyse (const AnalyseParams p)
     const float* tail = p.tail_in + track * (long) (N - H);
 
     if (! FX_TW1_GLOBAL) for (int i = t; i < D::TW1_LEN; i += T) sm.tw1[i] = p.tw1[i];
-    if (D::TW2_POWERS) { for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[((1 << (i >> 4)) - 1) * 16 + (i & 15)]; }      // rows k2 = 1, 2, 4, 8
+    if (D::TW2_POWERS)                                                                            // rows k2 = 1, 2, 4, 8, into the ring's holes
+    {
+        static_assert (D::TW2_LEN / 2 <= N / 32, "one hole per two stage-2 twiddles");
+        for (int i = t; i < D::TW2_LEN; i += T)
+            reinterpret_cast<float2*> (sm.ring + 32)[18 * (i >> 1) + (i & 1)] = p.tw2[((1 << (i >> 4)) - 1) * 16 + (i & 15)];
+    }
     else               { for (int i = t; i < D::TW2_LEN; i += T) sm.tw2[i] = p.tw2[i]; }
-    if (t == 0) { mbar_init (&sm.mbar, 1); sm.tw1f = p.tw1f; }
+    if (t == 0) { mbar_init (&sm.mbar, T); sm.tw1f = p.tw1f; }             // every thread arrives once per hop block (its copies, or its stores)
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -341,31 +372,18 @@ k_analyse (const AnalyseParams p)
     // frame f (call-relative) ends with hop block f of this call = absolute hop first_hop + f
     {
         const long j_new = p.first_hop + f_begin;
-        uint32_t bulk_bytes = 0;
         for (int b = 0; b < NB; ++b)
         {
             const long j = j_new - (NB - 1) + b;                 // absolute hop index
-            float* dst = sm.ring + (int) ((j * H) & (N - 1));
+            const int base = (int) ((j * H) & (N - 1));
             const float* g = nullptr;
             if (j >= p.first_hop)                  g = src + (j - p.first_hop) * H;
             else if (j >= 0)                       g = tail + (j - (p.first_hop - (NB - 1))) * H;
-            if (g == nullptr)      { _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = 0.0f; }      // before the stream started (RealTimeAudioAnalysis.h:202)
-            else if (! p.use_bulk) { _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = g[i]; }
-            else                   bulk_bytes += (uint32_t) H * 4u;
+            if (g == nullptr)      { _Pragma ("unroll 1") for (int i = t; i < H; i += T) sm.ring[sk32 (base + i)] = 0.0f; }      // before the stream started (RealTimeAudioAnalysis.h:202)
+            else if (! p.use_bulk) { _Pragma ("unroll 1") for (int i = t; i < H; i += T) sm.ring[sk32 (base + i)] = g[i]; }
+            else                   { _Pragma ("unroll 1") for (int k = 4 * t; k < H; k += 4 * T) cp_async16 (&sm.ring[sk32 (base + k)], g + k); }
         }
-        if (p.use_bulk && t == 0)
-        {
-            fence_proxy_async();
-            mbar_expect_tx (&sm.mbar, bulk_bytes);
-            for (int b = 0; b < NB; ++b)
-            {
-                const long j = j_new - (NB - 1) + b;
-                float* dst = sm.ring + (int) ((j * H) & (N - 1));
-                if (j >= p.first_hop)      bulk_g2s (dst, src + (j - p.first_hop) * H, (uint32_t) H * 4u, &sm.mbar);
-                else if (j >= 0)           bulk_g2s (dst, tail + (j - (p.first_hop - (NB - 1))) * H, (uint32_t) H * 4u, &sm.mbar);
-            }
-        }
-        if (! p.use_bulk && t == 0) mbar_arrive (&sm.mbar);
+        cp_async_arrive (&sm.mbar);
         __syncthreads();
     }
 
@@ -377,6 +395,7 @@ k_analyse (const AnalyseParams p)
     int first_nonsilent = -1;
     const int lower_portion = M / 5;                                // SpectralCharacteristics.h:65
     const int b0 = 8 * t;                                           // this thread's 8 consecutive bins
+    const int pb0 = sk32 (b0);                                      // ... and where they start in the skewed P / Re A array
     const double inv_m = 1.0 / (double) M;                          // exact: M is a power of two
     // where this thread's runs of the spectrum live in the exchange buffer (fx_fft.cuh: zpos): its 8 bins b0 + j and their
     // mirrors N - b0 - j (j = 0 pairs with (N - b0) & (N - 1), j >= 1 with the run that starts at N - b0 - 8), and its 16 lags
@@ -411,7 +430,7 @@ k_analyse (const AnalyseParams p)
         // fp32 first, 1e-7 relative on a feature compared at 1e-4).
         {
             const int n0 = 16 * t;
-            const int r0 = (int) ((a0 + n0) & (N - 1));                                           // multiple of 16
+            const int r0 = sk32 ((int) ((a0 + n0) & (N - 1)));                                    // 16 consecutive samples stay inside a 32-float group
             const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
             float xs[16], ys[16];
             float sq0 = 0.0f, sq1 = 0.0f;
@@ -436,7 +455,7 @@ k_analyse (const AnalyseParams p)
             // chain the scheduler can interleave with the recurrence above, instead of a divergent tail behind it
             float ywarm = 0.0f;
             {
-                const int rpw = (int) ((a0 + 16 * (t & ~31) - 12) & (N - 1));
+                const int rpw = sk32 ((int) ((a0 + 16 * (t & ~31) - 12) & (N - 1)));
                 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                 {
@@ -455,7 +474,7 @@ k_analyse (const AnalyseParams p)
                 if (t != 0)
                 {
                     // the left neighbour lives in another warp: warm up over its last 12 samples (e^(-pi/2)^12 = 6.5e-9)
-                    const int rp = (int) ((a0 + n0 - 12) & (N - 1));
+                    const int rp = sk32 ((int) ((a0 + n0 - 12) & (N - 1)));
                     #pragma unroll
                     for (int q = 0; q < 3; ++q)
                     {
@@ -527,9 +546,9 @@ k_analyse (const AnalyseParams p)
                 pq[j] = __fmul_rn (reC, reC);
                 psum = fmaf (pq[j], pq[j], psum);
             }
-            *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (pq[0], pq[1], pq[2], pq[3]);
-            *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (pq[4], pq[5], pq[6], pq[7]);
-            if (t == 0) { const float cm = 2.0f * sm.ex[zpos<R1> (M)].y; sm.pa[M] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
+            *reinterpret_cast<float4*> (&sm.pa[pb0])     = make_float4 (pq[0], pq[1], pq[2], pq[3]);
+            *reinterpret_cast<float4*> (&sm.pa[pb0 + 4]) = make_float4 (pq[4], pq[5], pq[6], pq[7]);
+            if (t == 0) { const float cm = 2.0f * sm.ex[zpos<R1> (M)].y; sm.pa[sk32 (M)] = __fmul_rn (cm, cm); }      // C[N/2] is real and pairs with itself
         }
 
         // RMS (RealTimeAnalyser.h:207-208)
@@ -723,15 +742,20 @@ k_analyse (const AnalyseParams p)
                 k2 = max (-120, min (120, k2));
                 pscale = __int_as_float ((k2 + 127) << 23);
             }
-            const int rb = (int) ((a0 + t) & (N - 1));
+            // sample a0 + t + c of the ring and P[c + t] (c < M) or P[N - c - t] (P is even: P[N - n] = P[n]); every c is a
+            // multiple of 32, so the skewed positions are a per-thread base plus a compile-time offset (ring: modulo the ring)
+            const int rg = (int) ((a0 + t) >> 5) & (N / 32 - 1), rl = (int) ((a0 + t) & 31);
+            const int pa_up = 36 * warp + lane;                                                   // sk32 (c + t) - 36 (c / 32)
+            const int pa_dn = -36 * warp - lane - (lane ? 4 : 0);                                 // sk32 (N - c - t) - 36 ((N - c) / 32)
             #pragma unroll
             for (int q = 0; q < Q1; ++q)
                 #pragma unroll
                 for (int n1 = 0; n1 < R1; ++n1)
                 {
                     const int c = n1 * 256 + T * q;
-                    const int idx = (c < M) ? c + t : (N - c) - t;                                // P is even: P[N - n] = P[n]
-                    io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[(rb + c) & (N - 1)], sm.pa[idx]), make_float2 (gain, pscale));
+                    const int pidx = (c < M) ? pa_up + 36 * (c / 32) : pa_dn + 36 * ((N - c) / 32);
+                    const int ridx = 36 * ((rg + c / 32) & (N / 32 - 1)) + rl;
+                    io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[ridx], sm.pa[pidx]), make_float2 (gain, pscale));
                 }
         }
         // No barrier here: stage 1 of the transform stores to this thread's own slots of the exchange buffer, which nobody
@@ -753,22 +777,14 @@ k_analyse (const AnalyseParams p)
         if (f + 1 < f_end)
         {
             const long jn = j_new + 1;
-            float* dst = sm.ring + (int) ((jn * H) & (N - 1));
+            const int base = (int) ((jn * H) & (N - 1));
             const float* g = src + (jn - p.first_hop) * H;
-            if (p.use_bulk)
-            {
-                if (t == 0)
-                {
-                    fence_proxy_async();
-                    mbar_expect_tx (&sm.mbar, (uint32_t) H * 4u);
-                    bulk_g2s (dst, g, (uint32_t) H * 4u, &sm.mbar);
-                }
-            }
-            else
-            {
-                _Pragma ("unroll 1") for (int i = t; i < H; i += T) dst[i] = g[i];       // visible after the barriers below
-                if (t == 0) mbar_arrive (&sm.mbar);
-            }
+            // (the skewed ring takes the block as 16-byte pieces, one or two per thread: asynchronous copies without register
+            // staging -- LDGSTS -- whose completion arrives at the mbarrier the next frame waits on.  A bulk copy per 128-byte run
+            // was measured 5 % slower at N = 2048 / 1024: 32 small TMA requests per frame cost more than the conflicts they remove)
+            if (p.use_bulk) { _Pragma ("unroll 1") for (int k = 4 * t; k < H; k += 4 * T) cp_async16 (&sm.ring[sk32 (base + k)], g + k); }
+            else            { _Pragma ("unroll 1") for (int i = t; i < H; i += T) sm.ring[sk32 (base + i)] = g[i]; }
+            cp_async_arrive (&sm.mbar);
         }
 
         // =========================== pitch: cumulative normalised difference + lag search ==============
@@ -792,8 +808,8 @@ k_analyse (const AnalyseParams p)
                 float ra[8];
                 #pragma unroll
                 for (int j = 0; j < 8; ++j) ra[j] = sm.ex[zb_own + zrun<R1> (j)].x;
-                *reinterpret_cast<float4*> (&sm.pa[b0])     = make_float4 (ra[0], ra[1], ra[2], ra[3]);
-                *reinterpret_cast<float4*> (&sm.pa[b0 + 4]) = make_float4 (ra[4], ra[5], ra[6], ra[7]);
+                *reinterpret_cast<float4*> (&sm.pa[pb0])     = make_float4 (ra[0], ra[1], ra[2], ra[3]);
+                *reinterpret_cast<float4*> (&sm.pa[pb0 + 4]) = make_float4 (ra[4], ra[5], ra[6], ra[7]);
             }
             double inc = (double) runf;
             #pragma unroll
@@ -850,12 +866,12 @@ k_analyse (const AnalyseParams p)
         // barrier every thread overwrites its own 8 bins of the array with the normalised magnitudes.
         float ar[11];
         {
-            const float4 a0v = *reinterpret_cast<const float4*> (&sm.pa[b0]);
-            const float4 a1v = *reinterpret_cast<const float4*> (&sm.pa[b0 + 4]);
+            const float4 a0v = *reinterpret_cast<const float4*> (&sm.pa[pb0]);
+            const float4 a1v = *reinterpret_cast<const float4*> (&sm.pa[pb0 + 4]);
             ar[2] = a0v.x; ar[3] = a0v.y; ar[4] = a0v.z; ar[5] = a0v.w; ar[6] = a1v.x; ar[7] = a1v.y; ar[8] = a1v.z; ar[9] = a1v.w;
-            ar[0] = (b0 >= 2) ? sm.pa[b0 - 2] : 0.0f;
-            ar[1] = (b0 >= 1) ? sm.pa[b0 - 1] : 0.0f;
-            ar[10] = (b0 + 8 < M) ? sm.pa[b0 + 8] : 0.0f;
+            ar[0] = (b0 >= 2) ? sm.pa[sk32 (b0 - 2)] : 0.0f;
+            ar[1] = (b0 >= 1) ? sm.pa[sk32 (b0 - 2) + 1] : 0.0f;
+            ar[10] = (b0 + 8 < M) ? sm.pa[sk32 (b0 + 8)] : 0.0f;
             double hsum = 0.0; float hmaxre = 0.0f;
             #pragma unroll
             for (int j = 0; j < 8; ++j) { const double re = (double) ar[2 + j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[2 + j])); }
@@ -1036,7 +1052,7 @@ k_analyse (const AnalyseParams p)
                     // bin 0 (:224 start = frpb / 2): the start edge's ratio is exactly twice the end edge's, and that one is N / lag >= 1,
                     // so their floors always differ (:232) and the bin contributes nothing
                     if (bin == 0) continue;
-                    const double re = (double) sm.pa[bin];                                        // still Re A: this thread's own bins
+                    const double re = (double) sm.pa[pb0 + j];                                    // still Re A: this thread's own bins
                     const double mg = re * re;
                     // :223-239 compares floor (higher / lower) for the two edges of the bin, start = bin frpb and end = (bin + 1) frpb,
                     // against f0 = sample rate / lag.  Up to an ulp of fp64 rounding these ratios are the rationals bin lag / N
@@ -1108,8 +1124,8 @@ k_analyse (const AnalyseParams p)
                     // monotone, so it is the normalised value of the largest |Re A|, which is what the record keeps; K1b
                     // normalises and sums the 18 terms in the reference's order.
                     // (the window [st, en) holds at most bins c - 2 .. c + 1: four independent loads, indices clamped into the window)
-                    const float m0 = fabsf (sm.pa[her_bin]), m1 = fabsf (sm.pa[max (her_bin - 2, st)]), m2 = fabsf (sm.pa[max (her_bin - 1, st)]);
-                    const float m3 = fabsf (sm.pa[min (her_bin + 1, en - 1)]);
+                    const float m0 = fabsf (sm.pa[sk32 (her_bin)]), m1 = fabsf (sm.pa[sk32 (max (her_bin - 2, st))]), m2 = fabsf (sm.pa[sk32 (max (her_bin - 1, st))]);
+                    const float m3 = fabsf (sm.pa[sk32 (min (her_bin + 1, en - 1))]);
                     mx = fmaxf (fmaxf (m0, m1), fmaxf (m2, m3));
                 }
                 if (lane < 18) rec->her_mx[lane] = mx;
@@ -1189,7 +1205,7 @@ k_analyse (const AnalyseParams p)
         // the newest N - H samples of the stream become the next call's overlap
         const long a_end = (p.first_hop + f_end) * (long) H;
         float* to = p.tail_out + track * (long) (N - H);
-        for (int i = t; i < N - H; i += T) to[i] = sm.ring[(int) ((a_end - (N - H) + i) & (N - 1))];
+        for (int i = t; i < N - H; i += T) to[i] = sm.ring[sk32 ((int) ((a_end - (N - H) + i) & (N - 1)))];
     }
 }
 

@@ -270,7 +270,7 @@ fx_status run_range (fx_engine* e, int t0, int nt, int n_chunks, int flip, long 
     a.first_hop = frames_done;
     a.n_frames = (int) frames; a.frames_per_chunk = fpc; a.n_chunks = n_chunks;
     a.hop = e->H; a.log2_hop = e->log2_hop;
-    a.use_bulk = (((uintptr_t) d_audio & 15u) == 0 && (track_stride % 4) == 0 && (e->H % 4) == 0) ? 1 : 0;
+    a.use_bulk = (((uintptr_t) d_audio & 15u) == 0 && (track_stride % 4) == 0 && (e->H % 4) == 0) ? 1 : 0;       // the kernel copies 16-byte pieces (cp.async)
     a.want_margins = d_diag != nullptr ? 1 : 0;
     a.gain = e->d_gain + t0;
     a.sample_rate = e->cfg.sample_rate; a.bin_var = e->bin_var; a.iir_c1 = e->iir_c1; a.iir_c2 = e->iir_c2;

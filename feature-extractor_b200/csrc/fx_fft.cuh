@@ -209,6 +209,10 @@ template <int R1> struct FftDims
     // stage-2 twiddles by powers: the shared-memory copy holds only the rows k2 = 1, 2, 4, 8 (in that order)
     static constexpr bool TW2_POWERS = FX_TW2_POWERS == 1 || (FX_TW2_POWERS == 2 && R1 == 16);
     static constexpr int TW2_LEN = TW2_POWERS ? 4 * 16 : TW2_FULL;
+    // ... and it lives in the 16-byte holes of the caller's skewed sample ring (fx_analyse.cu: one unused float4 behind every 32
+    // floats): element e = row * 16 + n3 sits in hole e / 2, slot e % 2, holes 36 floats = 18 float2 apart.  The 16 lanes of a
+    // half warp read 8 holes, i.e. 8 different 16-byte bank groups: conflict free like the dense table.
+    static constexpr int TW2_HOLE_ROW = 8 * 18;        // float2 distance between the rows k2 = 1, 2, 4, 8 of one n3
 };
 
 // Stage 1 on v (slot q * R1 + n1 = input n1 of butterfly q), then twiddle and store to ex.
@@ -269,7 +273,8 @@ __device__ __forceinline__ void fft_stage2 (int t, float2* __restrict__ ex, cons
     float2 wp[16];
     if (kPowers)
     {
-        wp[1] = tw2[n3]; wp[2] = tw2[16 + n3]; wp[4] = tw2[2 * 16 + n3]; wp[8] = tw2[3 * 16 + n3];
+        const float2* th = tw2 + 18 * (n3 >> 1) + (n3 & 1);                                  // tw2: first hole of the ring
+        wp[1] = th[0]; wp[2] = th[D::TW2_HOLE_ROW]; wp[4] = th[2 * D::TW2_HOLE_ROW]; wp[8] = th[3 * D::TW2_HOLE_ROW];
         twiddle_powers<16> (wp);
     }
     #pragma unroll
