@@ -48,6 +48,51 @@
 #define FX_WARMUP_ALL_LANES 1
 #endif
 
+// v26 instruction trims (each switch restores the previous form for A/B builds; all but FX_FAST_EPS compute the same values):
+//   FX_GATHER_GROUPS  FFT-beta's ring gather takes one wrapped base per group of loads that cannot wrap inside (hop >= N / 4)
+//   FX_LAZY_CROSS     the position of a thread's first lag under the threshold is only looked for when its minimum is under it
+//   FX_FLUX_F32CMP    "magnitude rose" decided on |Re| (the magnitudes are exact squares), a predicated add instead of selects
+//   FX_PSUM_SLOT      the norm of P rides in the free eighth slot of pass 1's transposed butterfly
+//   FX_FAST_EPS       the flatness gate's eps = 0.01 log10 (9 rms + 1) from MUFU approximations (1e-6 relative: it gates bins
+//                     whose margin is reported anyway; K1b recomputes the RMS feature itself in double)
+#ifndef FX_GATHER_GROUPS
+#define FX_GATHER_GROUPS 1
+#endif
+#ifndef FX_LAZY_CROSS
+#define FX_LAZY_CROSS 1
+#endif
+#ifndef FX_FLUX_F32CMP
+#define FX_FLUX_F32CMP 0
+#endif
+#ifndef FX_PSUM_SLOT
+#define FX_PSUM_SLOT 0
+#endif
+#ifndef FX_FAST_EPS
+#define FX_FAST_EPS 0
+#endif
+// fp32 warp reductions of sums whose per-thread partials are fp32-accurate anyway (the cross-warp sums stay fp64):
+//   FX_RMS_F32    sum of squares of the frame (16 fp32 squares per thread)
+//   FX_HSUM_F32   harmonic magnitude sum (8 squares per thread)
+//   FX_PSCAN_F32  warp scan of the lag search's cumulative sum (the reference runs this sum in fp32 sequentially, :138-145)
+//   FX_INHARM_F32 inharmonicity sum (a few peaks per thread)
+//   FX_P1SUM_F32  pass 1's seven sums (fp64 per thread over its 8 bins, fp32 across the lanes)
+//   FX_MESCAN_F32 mantissa of the flatness product's warp scan (the exponent is an integer; the product only feeds pow (., 1 / count))
+#ifndef FX_RMS_F32
+#define FX_RMS_F32 1
+#endif
+#ifndef FX_HSUM_F32
+#define FX_HSUM_F32 1
+#endif
+#ifndef FX_PSCAN_F32
+#define FX_PSCAN_F32 1
+#endif
+#ifndef FX_INHARM_F32
+#define FX_INHARM_F32 1
+#endif
+#ifndef FX_MESCAN_F32
+#define FX_MESCAN_F32 1
+#endif
+
 namespace fx {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -197,7 +242,7 @@ template <int K> __device__ __forceinline__ int warp_sum_slot (int lane)
     for (int b = 0; (K >> (b + 1)) > 0; ++b) idx += ((lane >> b) & 1) * (K >> (b + 1));
     return idx;
 }
-template <int K> __device__ __forceinline__ void warp_sum_t (double (&v)[K], int lane)
+template <int K, typename V> __device__ __forceinline__ void warp_sum_t (V (&v)[K], int lane)
 {
     int b = 0;
     #pragma unroll
@@ -207,8 +252,8 @@ template <int K> __device__ __forceinline__ void warp_sum_t (double (&v)[K], int
         #pragma unroll
         for (int i = 0; i < half; ++i)
         {
-            const double keep = up ? v[i + half] : v[i];
-            const double send = up ? v[i] : v[i + half];
+            const V keep = up ? v[i + half] : v[i];
+            const V send = up ? v[i] : v[i + half];
             v[i] = keep + __shfl_xor_sync (0xffffffffu, send, 1 << b);
         }
     }
@@ -442,9 +487,14 @@ k_analyse (const AnalyseParams p)
                 sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
             }
             {
+#if FX_RMS_F32
+                const float wsq = warp_sumf (sq0 + sq1);
+                if (lane == 0) sm.rms[warp] = (double) wsq * ((double) gain * (double) gain);      // AudioDataCollector.h:88 applies the gain
+#else
                 double r1[1] = { (double) (sq0 + sq1) * ((double) gain * (double) gain) };       // AudioDataCollector.h:88 applies the gain
                 warp_sum<1> (r1);
                 if (lane == 0) sm.rms[warp] = r1[0];
+#endif
             }
             float y = (t == 0) ? __fmul_rn (xs[0], gain) : __fmul_rn (xs[0], c1g);               // y[0] = x[0]
             ys[0] = y;
@@ -560,8 +610,14 @@ k_analyse (const AnalyseParams p)
             rms_sum += r2.x; rms_sum += r2.y;
         }
         // K1b recomputes both in double for the RMS feature; here they only set the flatness gate, whose margin is reported
+#if FX_FAST_EPS
+        float rms, log_rms;
+        asm ("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rms) : "f"((float) (rms_sum * (1.0 / (double) N))));
+        log_rms = __log2f (fmaf (rms, 9.0f, 1.0f)) * 0.30102999566f;
+#else
         const float rms = __fsqrt_rn ((float) (rms_sum * (1.0 / (double) N)));
         const float log_rms = log10f (__fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));
+#endif
         const double eps = 0.01 * (double) log_rms;                                               // SpectralCharacteristics.h:108
 
         // =========================== spectral features, pass 1 ========================================
@@ -588,7 +644,11 @@ k_analyse (const AnalyseParams p)
                 const double mg = re * re;                                                       // :72-73  Re^2
                 const double pm = (double) pr[j] * (double) pr[j];
                 const double diff = mg - pm;                                                     // :76-79
+#if FX_FLUX_F32CMP
+                if (fabsf (cr[j]) > fabsf (pr[j])) flux += diff;                                 // mg > pm: both are exact squares
+#else
                 if (diff > 0.0) flux += diff;
+#endif
                 mag_sum += mg;
                 if (bin <= lower_portion) lhr += mg;                                             // :86-87
                 if (mg > eps)                                                                    // :89-94
@@ -608,15 +668,38 @@ k_analyse (const AnalyseParams p)
                 maxre = fmaxf (maxre, fabsf (cr[j]));
             }
             lprod = me_from (mprod); lprod.e += esum;
-            double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, 0.0 };
+#if FX_P1SUM_F32
+            float s8[8] = { (float) mag_sum, (float) weighted, (float) flux, (float) lhr, (float) s2, (float) s4, (float) flat_sum, FX_PSUM_SLOT ? psum : 0.0f };
+#else
+            double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, FX_PSUM_SLOT ? (double) psum : 0.0 };
+#endif
             warp_sum_t<8> (s8, lane);
             const int wcount = warp_addi (count);
             const float wmax = warp_max_nonneg (maxre);
             const float wraw = warp_max_nonneg (rawmax);
+#if FX_PSUM_SLOT
+            const float wps = (float) __shfl_sync (0xffffffffu, s8[0], 7);                       // slot 7's total lives in lanes = 7 mod 8
+#else
             const float wps = warp_sumf (psum);
+#endif
             float wmar = 1.0f;
             if (MG) wmar = warp_min_nonneg (fminf (gate_d * gate_inv, 0.5f));
             // inclusive warp scan of the extended-range product, in bin order
+#if FX_MESCAN_F32
+            struct { float m; int e; } incf = { (float) lprod.m, lprod.e };                      // m in [0.5, 1]
+            #pragma unroll
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                const float om = __shfl_up_sync (0xffffffffu, incf.m, off); const int oe = __shfl_up_sync (0xffffffffu, incf.e, off);
+                if (lane >= off)
+                {
+                    float m = om * incf.m; int e = oe + incf.e;                                   // m in [0.25, 1]
+                    if (m < 0.5f) { m *= 2.0f; e -= 1; }
+                    incf.m = m; incf.e = e;
+                }
+            }
+            ME inc; inc.m = (double) incf.m; inc.e = incf.e;
+#else
             ME inc = lprod;
             #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
@@ -624,6 +707,7 @@ k_analyse (const AnalyseParams p)
                 ME o; o.m = __shfl_up_sync (0xffffffffu, inc.m, off); o.e = __shfl_up_sync (0xffffffffu, inc.e, off);
                 if (lane >= off) inc = me_mul (o, inc);
             }
+#endif
             ME exc; exc.m = __shfl_up_sync (0xffffffffu, inc.m, 1); exc.e = __shfl_up_sync (0xffffffffu, inc.e, 1);
             if (lane == 0) exc = me_one();
             lprod = exc;                                                                         // lane-exclusive prefix within the warp
@@ -637,12 +721,12 @@ k_analyse (const AnalyseParams p)
                 *reinterpret_cast<double2*> (&sm.scan[warp]) = make_double2 (inc.m, __hiloint2double (0, inc.e));
                 wp->scan_m = inc.m; wp->scan_e = inc.e;
             }
-            if (lane < 8) wp->p1[warp_sum_slot<8> (lane)] = s8[0];
+            if (lane < 8) wp->p1[warp_sum_slot<8> (lane)] = (double) s8[0];
             if (lane == 0)
             {
                 wp->count = wcount; wp->rawmax = wraw;
                 // S0: every thread needs the magnitude sum
-                *reinterpret_cast<double2*> (&sm.p1s[warp]) = make_double2 (s8[0], __hiloint2double (__float_as_int (wps), __float_as_int (wmax)));
+                *reinterpret_cast<double2*> (&sm.p1s[warp]) = make_double2 ((double) s8[0], __hiloint2double (__float_as_int (wps), __float_as_int (wmax)));
                 if (MG) sm.fmins[0][warp] = wmar;
             }
         }
@@ -747,16 +831,39 @@ k_analyse (const AnalyseParams p)
             const int rg = (int) ((a0 + t) >> 5) & (N / 32 - 1), rl = (int) ((a0 + t) & 31);
             const int pa_up = 36 * warp + lane;                                                   // sk32 (c + t) - 36 (c / 32)
             const int pa_dn = -36 * warp - lane - (lane ? 4 : 0);                                 // sk32 (N - c - t) - 36 ((N - c) / 32)
-            #pragma unroll
-            for (int q = 0; q < Q1; ++q)
+            if (FX_GATHER_GROUPS && NB <= 4)
+            {
+                // the window starts at a multiple of the hop: with hop >= N / 4 the ring wraps at a multiple of N / 4 samples, never
+                // inside a quarter of the window -- one wrapped base per quarter, compile-time offsets inside it
                 #pragma unroll
-                for (int n1 = 0; n1 < R1; ++n1)
+                for (int g = 0; g < 4; ++g)
                 {
-                    const int c = n1 * 256 + T * q;
-                    const int pidx = (c < M) ? pa_up + 36 * (c / 32) : pa_dn + 36 * ((N - c) / 32);
-                    const int ridx = 36 * ((rg + c / 32) & (N / 32 - 1)) + rl;
-                    io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[ridx], sm.pa[pidx]), make_float2 (gain, pscale));
+                    const float* rq = sm.ring + 36 * ((rg + g * (N / 128)) & (N / 32 - 1)) + rl;
+                    #pragma unroll
+                    for (int q = 0; q < Q1; ++q)
+                        #pragma unroll
+                        for (int i = 0; i < R1 / 4; ++i)
+                        {
+                            const int n1 = g * (R1 / 4) + i;
+                            const int c = n1 * 256 + T * q;
+                            const int pidx = (c < M) ? pa_up + 36 * (c / 32) : pa_dn + 36 * ((N - c) / 32);
+                            io.v[q * R1 + n1] = f2mul (make_float2 (rq[36 * ((c - g * (N / 4)) / 32)], sm.pa[pidx]), make_float2 (gain, pscale));
+                        }
                 }
+            }
+            else
+            {
+                #pragma unroll
+                for (int q = 0; q < Q1; ++q)
+                    #pragma unroll
+                    for (int n1 = 0; n1 < R1; ++n1)
+                    {
+                        const int c = n1 * 256 + T * q;
+                        const int pidx = (c < M) ? pa_up + 36 * (c / 32) : pa_dn + 36 * ((N - c) / 32);
+                        const int ridx = 36 * ((rg + c / 32) & (N / 32 - 1)) + rl;
+                        io.v[q * R1 + n1] = f2mul (make_float2 (sm.ring[ridx], sm.pa[pidx]), make_float2 (gain, pscale));
+                    }
+            }
         }
         // No barrier here: stage 1 of the transform stores to this thread's own slots of the exchange buffer, which nobody
         // reads between the barrier above (the split is complete) and the barrier inside the transform.
@@ -800,7 +907,7 @@ k_analyse (const AnalyseParams p)
             {
                 const float d = sm.ex[zl_own + zrun<R1> (j)].y + sm.ex[j == 0 ? zl_self : zl_mirror + zrun<R1> (16 - j)].y;     // Z[s] + Z[N - s]: 2 * 2^k * D[s]
                 if (MG) dv[j] = d;
-                av[j] = __fmul_rn (__fmul_rn (d, d), s0f + (float) j);                            // s = 0 contributes 0
+                av[j] = __fmul_rn (__fmul_rn (d, d), __fadd_rn (s0f, (float) j));                 // s = 0 contributes 0 (one FADD: the sum is exact)
                 runf += av[j];
             }
             // Re A of this thread's 8 bins moves to the P / Re A array (P was consumed by the transform)
@@ -811,6 +918,18 @@ k_analyse (const AnalyseParams p)
                 *reinterpret_cast<float4*> (&sm.pa[pb0])     = make_float4 (ra[0], ra[1], ra[2], ra[3]);
                 *reinterpret_cast<float4*> (&sm.pa[pb0 + 4]) = make_float4 (ra[4], ra[5], ra[6], ra[7]);
             }
+#if FX_PSCAN_F32
+            float inc = runf;
+            #pragma unroll
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                const float o = __shfl_up_sync (0xffffffffu, inc, off);
+                if (lane >= off) inc += o;
+            }
+            const float excf = __shfl_up_sync (0xffffffffu, inc, 1);
+            seg_exc = lane == 0 ? 0.0 : (double) excf;
+            if (lane == 31) sm.pscan[warp] = (double) inc;
+#else
             double inc = (double) runf;
             #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
@@ -821,6 +940,7 @@ k_analyse (const AnalyseParams p)
             seg_exc = __shfl_up_sync (0xffffffffu, inc, 1);
             if (lane == 0) seg_exc = 0.0;
             if (lane == 31) sm.pscan[warp] = inc;
+#endif
             if (MG && t == 0) sm.d0 = dv[0];
         }
         __syncthreads();
@@ -851,10 +971,21 @@ k_analyse (const AnalyseParams p)
                 c_before = c;
                 if (j >= 2 || t != 0)                                                             // the search starts at s = 2 (:169)
                 {
+#if ! FX_LAZY_CROSS
                     if (c < 0.01f) cross |= 1u << j;                                              // :176
+#endif
                     best = fminf (best, c);                                                       // :171-175 (its index only matters when no lag crosses: found then)
                 }
             }
+#if FX_LAZY_CROSS
+            // :176 some lag of this thread is under the threshold iff its minimum is: only then (few threads of a frame) look for the first
+            if (best < 0.01f)
+            {
+                #pragma unroll
+                for (int j = 15; j >= 0; --j)
+                    if ((j >= 2 || t != 0) && workg[17 * t + j] < 0.01f) cross = 1u << j;        // (this thread's own stores)
+            }
+#endif
             sm.ndm[t] = (unsigned short) nd_mask;
             if (cross != 0u) first_cross = (unsigned) (16 * t + __ffs ((int) cross) - 1);
             // smallest cnd of the warp (cnd >= 0 orders like its bit pattern)
@@ -872,11 +1003,19 @@ k_analyse (const AnalyseParams p)
             ar[0] = (b0 >= 2) ? sm.pa[sk32 (b0 - 2)] : 0.0f;
             ar[1] = (b0 >= 1) ? sm.pa[sk32 (b0 - 2) + 1] : 0.0f;
             ar[10] = (b0 + 8 < M) ? sm.pa[sk32 (b0 + 8)] : 0.0f;
-            double hsum = 0.0; float hmaxre = 0.0f;
+            float hmaxre = 0.0f;
+#if FX_HSUM_F32
+            float hsf = 0.0f;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) { hsf = fmaf (ar[2 + j], ar[2 + j], hsf); hmaxre = fmaxf (hmaxre, fabsf (ar[2 + j])); }
+            double s1[1] = { (double) warp_sumf (hsf) };
+#else
+            double hsum = 0.0;
             #pragma unroll
             for (int j = 0; j < 8; ++j) { const double re = (double) ar[2 + j]; hsum += re * re; hmaxre = fmaxf (hmaxre, fabsf (ar[2 + j])); }
             double s1[1] = { hsum };
             warp_sum<1> (s1);
+#endif
             const float wm = warp_max_nonneg (hmaxre);
             if (lane == 0)
             {
@@ -1096,8 +1235,12 @@ k_analyse (const AnalyseParams p)
             const float pkm = ulps_to_margin (pgap);
             // (the normalised magnitudes of :71-77 are not materialised: their sum is magnitudeSum / maxMagnitude up to fp64
             // rounding, and the few the harmonic energy terms look at are formed from Re A by the record stage)
+#if FX_INHARM_F32
+            double s1[1] = { (double) warp_sumf ((float) inharm) };
+#else
             double s1[1] = { inharm };
             warp_sum<1> (s1);
+#endif
             const int wnp = warp_addi (npeaks);
             if (lane == 0) { rec_w[warp].inharm = s1[0]; rec_w[warp].npeaks = wnp; }           // K1b sums the warps' parts
             if (MG) { const float wpk = warp_min_nonneg (pkm); if (lane == 0) sm.fmins[2][warp] = wpk; }

@@ -5,6 +5,12 @@
 #include <stdint.h>
 #include "../../include/fx_engine.h"
 
+// pass 1's sums are reduced across the lanes of a warp in fp32 (1) or fp64 (0): K1 and K2 (the flux of a chunk's first
+// non-silent frame) must agree on it, see fx_analyse.cu
+#ifndef FX_P1SUM_F32
+#define FX_P1SUM_F32 1
+#endif
+
 namespace fx {
 
 constexpr int kHistRows   = 32;   // raw feature rows carried between calls (10-tap smoothing + <=16-deep onset window + 5)

@@ -44,23 +44,41 @@ __global__ void __launch_bounds__ (256) k_flux_fix (const FluxFixParams p)
         if (fidx[c] >= 0) { prev = p.last_spec + (track * p.n_chunks + c) * (long) M; break; }
     const float* cur = p.first_spec + (track * p.n_chunks + chunk) * (long) M;
 
+    // The sum runs in K1's own order and precision, so that a frame's flux does not depend on where the chunk boundaries fall
+    // (tests: chunked, streamed and split calls are bit-identical): thread t takes bins 8 t .. 8 t + 7 in sequence (fp64), the
+    // lanes of a warp are added as K1's butterfly does (distances 1, 2, 4, 8, 16; in fp32 when K1 reduces pass 1 in fp32) and
+    // the warps as K1b's pairwise tree.  blockDim.x = M / 8 = the thread count of K1.
     double flux = 0.0;
-    for (int i = t; i < M; i += blockDim.x)
     {
-        const double c = (double) cur[i], q = (double) prev[i];
-        const double diff = c * c - q * q;                            // SpectralCharacteristics.h:76
-        if (diff > 0.0) flux += diff;                                 // :77-79
+        const float4 c0 = *reinterpret_cast<const float4*> (cur + 8 * t), c1 = *reinterpret_cast<const float4*> (cur + 8 * t + 4);
+        const float4 q0 = *reinterpret_cast<const float4*> (prev + 8 * t), q1 = *reinterpret_cast<const float4*> (prev + 8 * t + 4);
+        const float cv[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w }, qv[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const double c = (double) cv[j], q = (double) qv[j];
+            const double diff = c * c - q * q;                        // SpectralCharacteristics.h:76 (both products are exact)
+            if (diff > 0.0) flux += diff;                             // :77-79
+        }
     }
+#if FX_P1SUM_F32
+    float fl = (float) flux;
     #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) flux += __shfl_xor_sync (0xffffffffu, flux, off);
+    for (int off = 1; off < 32; off <<= 1) fl += __shfl_xor_sync (0xffffffffu, fl, off);
+    flux = (double) fl;
+#else
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1) flux += __shfl_xor_sync (0xffffffffu, flux, off);
+#endif
     if ((t & 31) == 0) wsum[t >> 5] = flux;
     __syncthreads();
     if (t == 0)
     {
-        double total = 0.0;
-        for (int w = 0; w < (int) (blockDim.x >> 5); ++w) total += wsum[w];
+        const int nw = (int) (blockDim.x >> 5);
+        for (int half = 1; half < nw; half <<= 1)
+            for (int w = 0; w < nw; w += 2 * half) wsum[w] += wsum[w + half];
         const float max_flux = (float) (M * (M + 1)) / 2.0f;          // :111
-        p.raw[(track * p.n_frames + fi) * FX_NUM_FEATURES + FX_FLUX] = (float) (total / (double) max_flux);
+        p.raw[(track * p.n_frames + fi) * FX_NUM_FEATURES + FX_FLUX] = (float) (wsum[0] / (double) max_flux);
     }
 }
 
@@ -68,7 +86,7 @@ cudaError_t launch_flux_fix (long n_tracks, const FluxFixParams& p, cudaStream_t
 {
     const long grid = n_tracks * p.n_chunks;
     if (grid <= 0) return cudaSuccess;
-    k_flux_fix<<<(unsigned) grid, 256, 0, stream>>> (p);
+    k_flux_fix<<<(unsigned) grid, (unsigned) (p.m / 8), 0, stream>>> (p);     // one thread per 8 bins, like K1
     return cudaGetLastError();
 }
 

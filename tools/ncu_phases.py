@@ -43,7 +43,7 @@ marks = [
     ("flatness prefetch + hop prefetch", find(src, "The flatness product's continuation (record stage, below) starts")),
     ("pitch (cnd scan, lag search)", find(src, "pitch: cumulative normalised difference + lag search")),
     ("harmonic (peaks, inharmonicity)", find(src, "The harmonic and sub-octave bins of f0")),
-    ("record stage", find(src, "the frame's record (what K1b needs), one part per warp")),
+    ("record stage", find(src, "---- what is left of the frame's record")),
     ("chunk epilogue", find(src, "---- chunk epilogue")),
     ("(end)", find(src, "K1b: the scalar tail of both analyser bodies")),
 ]
