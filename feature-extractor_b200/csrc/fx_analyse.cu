@@ -55,6 +55,10 @@
 //   FX_PSUM_SLOT      the norm of P rides in the free eighth slot of pass 1's transposed butterfly
 //   FX_FAST_EPS       the flatness gate's eps = 0.01 log10 (9 rms + 1) from MUFU approximations (1e-6 relative: it gates bins
 //                     whose margin is reported anyway; K1b recomputes the RMS feature itself in double)
+//   FX_B9_EARLY       the frame's last block barrier stands in front of the peak loop instead of behind it (see there)
+#ifndef FX_B9_EARLY
+#define FX_B9_EARLY 1
+#endif
 #ifndef FX_GATHER_GROUPS
 #define FX_GATHER_GROUPS 1
 #endif
@@ -1132,6 +1136,14 @@ k_analyse (const AnalyseParams p)
             const float wpm = warp_min_nonneg (pm);
             if (lane == 0) sm.pmins[0][warp] = wpm;
         }
+#if FX_B9_EARLY
+        // The frame's last block barrier: every read of the cnd values (the exchange buffer, which the next frame's filter pass
+        // overwrites) and of the descent masks (whose storage the record stage reuses) is behind it.  The peak loop below -- a
+        // thread-dependent number of peaks -- and the record stage then run into the next frame's filter pass without another
+        // barrier: their imbalance is absorbed once, at the barrier behind that pass, not twice.  What they read (this thread's
+        // registers, the P / Re A array, per-warp slots of earlier phases) is not written again before the next frame's pass 1.
+        __syncthreads();
+#endif
         // The harmonic and sub-octave bins of f0 = sample rate / lag come from a table built on the host with the reference's
         // own double arithmetic (PitchAnalyser.h:57, HarmonicCharacteristics.h:158-185): slot 0 stands for lag -1
         const int lag_slot = lag_i < 0 ? 0 : lag_i;
@@ -1245,7 +1257,7 @@ k_analyse (const AnalyseParams p)
             if (lane == 0) { rec_w[warp].inharm = s1[0]; rec_w[warp].npeaks = wnp; }           // K1b sums the warps' parts
             if (MG) { const float wpk = warp_min_nonneg (pkm); if (lane == 0) sm.fmins[2][warp] = wpk; }
         }
-        __syncthreads();
+        if (MG || ! FX_B9_EARLY) __syncthreads();                     // (the margins' per-warp minima reach the warp that records them)
         // ---- what is left of the frame's record ----------------------------------------------------------------------
         // The sums only K1b looks at left as per-warp partials where they were formed (the record's WarpParts); what remains here are the
         // values every thread holds (lag, harmonic sum and maximum), the 18 harmonic-energy maxima, the margins (MG) and the
