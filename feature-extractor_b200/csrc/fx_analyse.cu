@@ -59,6 +59,34 @@
 #ifndef FX_B9_EARLY
 #define FX_B9_EARLY 1
 #endif
+//   FX_PACKED_PASSES  filter / window / sum of squares, the split and the lag products on packed f32x2 instructions (two samples, two
+//                     parts or two lags per instruction, IEEE per half: the same values except the order of the 16-term run sums)
+#ifndef FX_PACKED_PASSES
+#define FX_PACKED_PASSES 2                // 0 never, 1 always, 2 for N <= 2048
+#endif
+#ifndef FX_PACK_SPLIT
+#define FX_PACK_SPLIT 0
+#endif
+#ifndef FX_PACK_LAG
+#define FX_PACK_LAG 1
+#endif
+//   FX_LHR_RANGE      the low-energy sum is the magnitude sum of the threads below the boundary bin; only the one thread that straddles it tests bins
+//   FX_PBASE_F32      the lag search's cumulative sum enters a segment as an fp32 sum of the fp32 warp totals (needs FX_PSCAN_F32)
+#ifndef FX_LHR_RANGE
+#define FX_LHR_RANGE 3                    // 0 never, 1 always, 3 for N >= 2048 (at N = 1024 it costs 0.8 %: spills)
+#endif
+#ifndef FX_PBASE_F32
+#define FX_PBASE_F32 1
+#endif
+//   FX_XWARP_F32      the cross-warp sums of fp32-accurate warp totals (rms, magnitude sum, harmonic sum) are fp32 chains: every thread
+//                     runs them right behind a barrier, and eight dependent DADDs are twice as long as eight FADDs
+//   FX_PREFIX_F32     likewise the mantissa of the flatness product's prefix over the preceding warps
+#ifndef FX_XWARP_F32
+#define FX_XWARP_F32 0
+#endif
+#ifndef FX_PREFIX_F32
+#define FX_PREFIX_F32 1
+#endif
 #ifndef FX_GATHER_GROUPS
 #define FX_GATHER_GROUPS 1
 #endif
@@ -66,10 +94,10 @@
 #define FX_LAZY_CROSS 1
 #endif
 #ifndef FX_FLUX_F32CMP
-#define FX_FLUX_F32CMP 0
+#define FX_FLUX_F32CMP 2                  // 0 never, 1 always, 2 for N <= 2048
 #endif
 #ifndef FX_PSUM_SLOT
-#define FX_PSUM_SLOT 0
+#define FX_PSUM_SLOT 2                    // 0 never, 1 always, 2 for N <= 2048
 #endif
 #ifndef FX_FAST_EPS
 #define FX_FAST_EPS 0
@@ -383,6 +411,12 @@ k_analyse (const AnalyseParams p)
     using S = Smem<R1>;
     constexpr int N = D::N, M = N / 2, T = D::T, NW = T / 32, Q1 = D::Q1;
     constexpr int LOG_N = R1 == 16 ? 12 : (R1 == 8 ? 11 : 10);
+    // measured per size (profiles/r02_v28_ab_*.txt): the packed filter pass and the |Re| flux test pay 1.2 - 2.1 % at N = 2048 / 1024
+    // (no spills there) and cost 2.7 % at N = 4096 (80-register budget: 40 bytes of spills)
+    constexpr bool kPackFilter = FX_PACKED_PASSES == 1 || (FX_PACKED_PASSES == 2 && R1 <= 8);
+    constexpr bool kFluxF32Cmp = FX_FLUX_F32CMP == 1 || (FX_FLUX_F32CMP == 2 && R1 <= 8);
+    constexpr bool kPsumSlot = FX_PSUM_SLOT == 1 || (FX_PSUM_SLOT == 2 && R1 <= 8);
+    constexpr bool kLhrRange = FX_LHR_RANGE == 1 || (FX_LHR_RANGE == 3 && R1 >= 8);
 
     S& sm = *reinterpret_cast<S*> (fx_smem_raw);
     float* workf = reinterpret_cast<float*> (sm.ex);          // fp32 view, skewed index phys (n)
@@ -481,29 +515,62 @@ k_analyse (const AnalyseParams p)
             const int n0 = 16 * t;
             const int r0 = sk32 ((int) ((a0 + n0) & (N - 1)));                                    // 16 consecutive samples stay inside a 32-float group
             const float c1 = p.iir_c1, c2 = p.iir_c2, c1g = __fmul_rn (c1, gain);
-            float xs[16], ys[16];
+            float xs[16], ys[16], xg[16], y;
             float sq0 = 0.0f, sq1 = 0.0f;
+            float2 sqp = make_float2 (0.0f, 0.0f);
             #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
                 const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
                 xs[4 * q] = x4.x; xs[4 * q + 1] = x4.y; xs[4 * q + 2] = x4.z; xs[4 * q + 3] = x4.w;
-                sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
+                if (kPackFilter)
+                {
+                    sqp = f2fma (make_float2 (x4.x, x4.y), make_float2 (x4.x, x4.y), sqp); sqp = f2fma (make_float2 (x4.z, x4.w), make_float2 (x4.z, x4.w), sqp);
+                }
+                else
+                {
+                    sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
+                }
+            }
+            if (kPackFilter)
+            {
+                sq0 = sqp.x; sq1 = sqp.y;
             }
             {
 #if FX_RMS_F32
                 const float wsq = warp_sumf (sq0 + sq1);
+#if FX_XWARP_F32
+                if (lane == 0) reinterpret_cast<float*> (sm.rms)[warp] = wsq;
+#else
                 if (lane == 0) sm.rms[warp] = (double) wsq * ((double) gain * (double) gain);      // AudioDataCollector.h:88 applies the gain
+#endif
 #else
                 double r1[1] = { (double) (sq0 + sq1) * ((double) gain * (double) gain) };       // AudioDataCollector.h:88 applies the gain
                 warp_sum<1> (r1);
                 if (lane == 0) sm.rms[warp] = r1[0];
 #endif
             }
-            float y = (t == 0) ? __fmul_rn (xs[0], gain) : __fmul_rn (xs[0], c1g);               // y[0] = x[0]
-            ys[0] = y;
-            #pragma unroll
-            for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (xs[j], c1g)); ys[j] = y; }
+            if (kPackFilter)
+            {
+                // (x gain, x c1 gain) of a sample in one packed multiply: the first half is the windowed path's sample, the second the filter's input
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    const float2 r = f2mul (make_float2 (xs[j], xs[j]), make_float2 (gain, c1g));
+                    xg[j] = r.x; ys[j] = r.y;
+                }
+                y = (t == 0) ? xg[0] : ys[0];                                                         // y[0] = x[0]
+                ys[0] = y;
+                #pragma unroll
+                for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, ys[j]); ys[j] = y; }
+            }
+            else
+            {
+                y = (t == 0) ? __fmul_rn (xs[0], gain) : __fmul_rn (xs[0], c1g);                     // y[0] = x[0]
+                ys[0] = y;
+                #pragma unroll
+                for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (xs[j], c1g)); ys[j] = y; }
+            }
 #if FX_WARMUP_ALL_LANES
             // every lane runs the warm-up of its WARP's first segment from broadcast loads (one wavefront each): an independent
             // chain the scheduler can interleave with the recurrence above, instead of a divergent tail behind it
@@ -545,15 +612,35 @@ k_analyse (const AnalyseParams p)
                                            3.132781128e-08f, 6.512412136e-09f };
             // Both windowed sequences go to the exchange buffer in natural (skewed) order as the packed input of FFT-alpha,
             // z[n] = x[n] w[n] + i y[n] w[n]: the transform's strided gather is then one 8-byte load per point.
-            #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            if (kPackFilter)
             {
-                if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
-                // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
-                // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
-                // (packed multiply: both sequences by the same ramp value.  What is stored is z / 2 -- see the split below)
-                const float w = fmaf ((float) j, wseg_d, wseg_0);
-                sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = f2mul (make_float2 (__fmul_rn (xs[j], gain), ys[j]), make_float2 (w, w));   // tpos (16 t + j)
+                // (two samples per instruction: the neighbour's decaying contribution, the ramp, and each sample's two sequences by its ramp value)
+                #pragma unroll
+                for (int j = 0; j < 16; j += 2)
+                {
+                    float2 y2 = make_float2 (ys[j], ys[j + 1]);
+                    if (j < 12) y2 = f2fma (make_float2 (kDecay[j], kDecay[j + 1]), make_float2 (yin, yin), y2);
+                    // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
+                    // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
+                    // (what is stored is z / 2 -- see the split below)
+                    const float2 w2 = f2fma (make_float2 ((float) j, (float) (j + 1)), make_float2 (wseg_d, wseg_d), make_float2 (wseg_0, wseg_0));
+                    float2* zp = &sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j];                                                   // tpos (16 t + j)
+                    zp[0] = f2mul (make_float2 (xg[j], y2.x), make_float2 (w2.x, w2.x));
+                    zp[1] = f2mul (make_float2 (xg[j + 1], y2.y), make_float2 (w2.y, w2.y));
+                }
+            }
+            else
+            {
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    if (j < 12) ys[j] = fmaf (kDecay[j], yin, ys[j]);
+                    // Bartlett ramp at n = n0 + j (RealTimeAudioAnalysis.h:148-149: w[n] = n * 2/N, w[N/2 + n] = 1 - n * 2/N): all 16
+                    // samples lie in the same half and every ramp value is a multiple of 2/N in [0, 1], exact in fp32
+                    // (packed multiply: both sequences by the same ramp value.  What is stored is z / 2 -- see the split below)
+                    const float w = fmaf ((float) j, wseg_d, wseg_0);
+                    sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j] = f2mul (make_float2 (__fmul_rn (xs[j], gain), ys[j]), make_float2 (w, w));   // tpos (16 t + j)
+                }
             }
         }
         __syncthreads();
@@ -593,7 +680,12 @@ k_analyse (const AnalyseParams p)
             {
                 const float2 zk = sm.ex[zb_own + zrun<R1> (j)];                                // Z[k], k = b0 + j
                 const float2 zn = sm.ex[j == 0 ? zb_self : zb_mirror + zrun<R1> (8 - j)];      // Z[(N - k) & (N - 1)]
+#if FX_PACK_SPLIT
+                const float2 sum = f2add (zk, zn);
+                const float reB = sum.x, reC = sum.y;
+#else
                 const float reB = zk.x + zn.x, reC = zk.y + zn.y;
+#endif
                 const float imB = zk.y - zn.y;
                 cr[j] = reB;
                 if (b0 < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
@@ -606,6 +698,16 @@ k_analyse (const AnalyseParams p)
         }
 
         // RMS (RealTimeAnalyser.h:207-208)
+#if FX_XWARP_F32 && FX_RMS_F32
+        float rms_sumf = 0.0f;
+        #pragma unroll
+        for (int w = 0; w < NW; w += 2)
+        {
+            const float2 r2 = *reinterpret_cast<const float2*> (&reinterpret_cast<const float*> (sm.rms)[w]);
+            rms_sumf += r2.x; rms_sumf += r2.y;
+        }
+        const double rms_sum = (double) rms_sumf * ((double) gain * (double) gain);                // AudioDataCollector.h:88 applies the gain
+#else
         double rms_sum = 0.0;
         #pragma unroll
         for (int w = 0; w < NW; w += 2)
@@ -613,6 +715,7 @@ k_analyse (const AnalyseParams p)
             const double2 r2 = *reinterpret_cast<const double2*> (&sm.rms[w]);
             rms_sum += r2.x; rms_sum += r2.y;
         }
+#endif
         // K1b recomputes both in double for the RMS feature; here they only set the flatness gate, whose margin is reported
 #if FX_FAST_EPS
         float rms, log_rms;
@@ -648,13 +751,16 @@ k_analyse (const AnalyseParams p)
                 const double mg = re * re;                                                       // :72-73  Re^2
                 const double pm = (double) pr[j] * (double) pr[j];
                 const double diff = mg - pm;                                                     // :76-79
-#if FX_FLUX_F32CMP
-                if (fabsf (cr[j]) > fabsf (pr[j])) flux += diff;                                 // mg > pm: both are exact squares
-#else
-                if (diff > 0.0) flux += diff;
-#endif
+                if (kFluxF32Cmp)
+                {
+                    if (fabsf (cr[j]) > fabsf (pr[j])) flux += diff;                                 // mg > pm: both are exact squares
+                }
+                else
+                {
+                    if (diff > 0.0) flux += diff;
+                }
                 mag_sum += mg;
-                if (bin <= lower_portion) lhr += mg;                                             // :86-87
+                if (! kLhrRange && bin <= lower_portion) lhr += mg;                              // :86-87
                 if (mg > eps)                                                                    // :89-94
                 {
                     flat_sum += mg;
@@ -671,21 +777,27 @@ k_analyse (const AnalyseParams p)
                 s4 = fma (mg, mg, s4);
                 maxre = fmaxf (maxre, fabsf (cr[j]));
             }
+            if (kLhrRange)
+            {
+                if (b0 + 7 <= lower_portion) lhr = mag_sum;                                       // :86-87 (the same additions in the same order)
+                else if (b0 <= lower_portion)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) if (b0 + j <= lower_portion) lhr += (double) cr[j] * (double) cr[j];
+                }
+            }
             lprod = me_from (mprod); lprod.e += esum;
 #if FX_P1SUM_F32
-            float s8[8] = { (float) mag_sum, (float) weighted, (float) flux, (float) lhr, (float) s2, (float) s4, (float) flat_sum, FX_PSUM_SLOT ? psum : 0.0f };
+            float s8[8] = { (float) mag_sum, (float) weighted, (float) flux, (float) lhr, (float) s2, (float) s4, (float) flat_sum, kPsumSlot ? psum : 0.0f };
 #else
-            double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, FX_PSUM_SLOT ? (double) psum : 0.0 };
+            double s8[8] = { mag_sum, weighted, flux, lhr, s2, s4, flat_sum, kPsumSlot ? (double) psum : 0.0 };
 #endif
             warp_sum_t<8> (s8, lane);
             const int wcount = warp_addi (count);
             const float wmax = warp_max_nonneg (maxre);
             const float wraw = warp_max_nonneg (rawmax);
-#if FX_PSUM_SLOT
-            const float wps = (float) __shfl_sync (0xffffffffu, s8[0], 7);                       // slot 7's total lives in lanes = 7 mod 8
-#else
-            const float wps = warp_sumf (psum);
-#endif
+            const float wps = kPsumSlot ? (float) __shfl_sync (0xffffffffu, s8[0], 7)              // slot 7's total lives in lanes = 7 mod 8
+                                        : warp_sumf (psum);
             float wmar = 1.0f;
             if (MG) wmar = warp_min_nonneg (fminf (gate_d * gate_inv, 0.5f));
             // inclusive warp scan of the extended-range product, in bin order
@@ -722,7 +834,7 @@ k_analyse (const AnalyseParams p)
             WarpPart* wp = &rec_w[warp];
             if (lane == 31)
             {
-                *reinterpret_cast<double2*> (&sm.scan[warp]) = make_double2 (inc.m, __hiloint2double (0, inc.e));
+                *reinterpret_cast<double2*> (&sm.scan[warp]) = make_double2 (inc.m, __hiloint2double (__float_as_int ((float) inc.m), inc.e));
                 wp->scan_m = inc.m; wp->scan_e = inc.e;
             }
             if (lane < 8) wp->p1[warp_sum_slot<8> (lane)] = (double) s8[0];
@@ -730,26 +842,56 @@ k_analyse (const AnalyseParams p)
             {
                 wp->count = wcount; wp->rawmax = wraw;
                 // S0: every thread needs the magnitude sum
+#if FX_XWARP_F32 && FX_P1SUM_F32
+                *reinterpret_cast<float4*> (&sm.p1s[warp]) = make_float4 ((float) s8[0], 0.0f, wmax, wps);
+#else
                 *reinterpret_cast<double2*> (&sm.p1s[warp]) = make_double2 ((double) s8[0], __hiloint2double (__float_as_int (wps), __float_as_int (wmax)));
+#endif
                 if (MG) sm.fmins[0][warp] = wmar;
             }
         }
         __syncthreads();
-        double mag_sum = 0.0;
+#if FX_XWARP_F32 && FX_P1SUM_F32
+        float mag_sum_acc = 0.0f;
+#else
+        double mag_sum_acc = 0.0;
+#endif
         float maxre_all = 0.0f, psum_all = 0.0f;
         ME prefix = me_one();
+        float pfm = 0.5f; int pfe = 1; (void) pfm; (void) pfe;
         // every thread needs the magnitude sum (silence gate), the largest |Re| (exponent budget below) and the norm of P;
         // everything else of the pass has already left for K1b as per-warp partials
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
+#if FX_XWARP_F32 && FX_P1SUM_F32
+            const float4 sl = *reinterpret_cast<const float4*> (&sm.p1s[w]);                      // one LDS.128: { s0, -, maxre, psum }
+            mag_sum_acc += sl.x;
+            maxre_all = fmaxf (maxre_all, sl.z);
+            psum_all += sl.w;
+#else
             const double2 sl = *reinterpret_cast<const double2*> (&sm.p1s[w]);                    // one LDS.128: { s0, (maxre, psum) }
-            mag_sum += sl.x;
+            mag_sum_acc += sl.x;
             maxre_all = fmaxf (maxre_all, __int_as_float (__double2loint (sl.y)));
             psum_all += __int_as_float (__double2hiint (sl.y));
+#endif
         }
+        const double mag_sum = (double) mag_sum_acc;
         #pragma unroll 1
-        for (int w = 0; w < warp; ++w) { const double2 sl = *reinterpret_cast<const double2*> (&sm.scan[w]); ME wt; wt.m = sl.x; wt.e = __double2loint (sl.y); prefix = me_mul (prefix, wt); }
+        for (int w = 0; w < warp; ++w)
+        {
+            const double2 sl = *reinterpret_cast<const double2*> (&sm.scan[w]);
+#if FX_PREFIX_F32 && FX_MESCAN_F32
+            const float wm = __int_as_float (__double2hiint (sl.y));                              // the warp total's fp32 mantissa rides in the slot's spare word
+            pfm *= wm; pfe += __double2loint (sl.y);
+            if (pfm < 0.5f) { pfm *= 2.0f; pfe -= 1; }
+#else
+            ME wt; wt.m = sl.x; wt.e = __double2loint (sl.y); prefix = me_mul (prefix, wt);
+#endif
+        }
+#if FX_PREFIX_F32 && FX_MESCAN_F32
+        prefix.m = (double) pfm; prefix.e = pfe;
+#endif
         prefix = me_mul (prefix, lprod);
         const double maxmag = (double) maxre_all * (double) maxre_all;
         const bool silent = ! (mag_sum > 0.05);                                                   // :121-123
@@ -906,6 +1048,23 @@ k_analyse (const AnalyseParams p)
         {
             const float s0f = (float) (16 * t);
             float runf = 0.0f;
+#if FX_PACK_LAG
+            float2 run2 = make_float2 (0.0f, 0.0f);
+            #pragma unroll
+            for (int j = 0; j < 16; j += 2)
+            {
+                // Z[s] + Z[N - s]: 2 * 2^k * D[s], two lags per instruction
+                const float2 za = make_float2 (sm.ex[zl_own + zrun<R1> (j)].y, sm.ex[zl_own + zrun<R1> (j + 1)].y);
+                const float2 zb = make_float2 (sm.ex[j == 0 ? zl_self : zl_mirror + zrun<R1> (16 - j)].y, sm.ex[zl_mirror + zrun<R1> (15 - j)].y);
+                const float2 d2 = f2add (za, zb);
+                if (MG) { dv[j] = d2.x; dv[j + 1] = d2.y; }
+                const float2 s2 = f2add (make_float2 (s0f, s0f), make_float2 ((float) j, (float) (j + 1)));
+                const float2 a2 = f2mul (f2mul (d2, d2), s2);                                     // s = 0 contributes 0
+                av[j] = a2.x; av[j + 1] = a2.y;
+                run2 = f2add (run2, a2);
+            }
+            runf = run2.x + run2.y;
+#else
             #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
@@ -914,6 +1073,7 @@ k_analyse (const AnalyseParams p)
                 av[j] = __fmul_rn (__fmul_rn (d, d), __fadd_rn (s0f, (float) j));                 // s = 0 contributes 0 (one FADD: the sum is exact)
                 runf += av[j];
             }
+#endif
             // Re A of this thread's 8 bins moves to the P / Re A array (P was consumed by the transform)
             {
                 float ra[8];
@@ -932,7 +1092,11 @@ k_analyse (const AnalyseParams p)
             }
             const float excf = __shfl_up_sync (0xffffffffu, inc, 1);
             seg_exc = lane == 0 ? 0.0 : (double) excf;
+#if FX_PBASE_F32
+            if (lane == 31) reinterpret_cast<float*> (sm.pscan)[warp] = inc;
+#else
             if (lane == 31) sm.pscan[warp] = (double) inc;
+#endif
 #else
             double inc = (double) runf;
             #pragma unroll
@@ -950,6 +1114,17 @@ k_analyse (const AnalyseParams p)
         __syncthreads();
         unsigned first_cross = 0xffffffffu, nd_mask = 0u, wfc, wbest;
         {
+#if FX_PBASE_F32 && FX_PSCAN_F32
+            float sumf = 0.0f;
+            #pragma unroll
+            for (int w = 0; w < NW; w += 2)
+            {
+                const float2 p2 = *reinterpret_cast<const float2*> (&reinterpret_cast<const float*> (sm.pscan)[w]);
+                if (w < warp) sumf += p2.x;
+                if (w + 1 < warp) sumf += p2.y;
+            }
+            sumf += (float) seg_exc;
+#else
             double base = seg_exc;
             #pragma unroll
             for (int w = 0; w < NW; w += 2)
@@ -960,6 +1135,7 @@ k_analyse (const AnalyseParams p)
             }
             // fp32 running sum inside the segment, as in the reference (:138-145), on top of the fp64 prefix
             float sumf = (float) base;
+#endif
             float best = 100.0f;
             unsigned cross = 0u;
             float c_before = 0.0f;
@@ -1023,7 +1199,11 @@ k_analyse (const AnalyseParams p)
             const float wm = warp_max_nonneg (hmaxre);
             if (lane == 0)
             {
+#if FX_XWARP_F32 && FX_HSUM_F32
+                *reinterpret_cast<float4*> (&sm.lags[warp]) = make_float4 ((float) s1[0], wm, __uint_as_float (wfc), __uint_as_float (wbest));
+#else
                 *reinterpret_cast<double2*> (&sm.lags[warp]) = make_double2 (s1[0], __hiloint2double ((int) wbest, (int) wfc));
+#endif
                 sm.hmaxs[warp] = wm;
             }
         }
@@ -1031,16 +1211,31 @@ k_analyse (const AnalyseParams p)
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
         unsigned s0 = 0xffffffffu;
         unsigned gbest = 0xffffffffu;                              // bit pattern of the smallest cnd of the search range
-        double hsum = 0.0; float hmaxre = 0.0f;
+#if FX_XWARP_F32 && FX_HSUM_F32
+        float hsum_acc = 0.0f;
+#else
+        double hsum_acc = 0.0;
+#endif
+        float hmaxre = 0.0f;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
+#if FX_XWARP_F32 && FX_HSUM_F32
+            const float4 sl = *reinterpret_cast<const float4*> (&sm.lags[w]);                     // one LDS.128: { hsum, largest |Re A|, first_cross, best }
+            s0 = min (s0, __float_as_uint (sl.z));
+            gbest = min (gbest, __float_as_uint (sl.w));
+            hsum_acc += sl.x;
+            hmaxre = fmaxf (hmaxre, sl.y);
+#else
             const double2 sl = *reinterpret_cast<const double2*> (&sm.lags[w]);                   // one LDS.128: { hsum, (first_cross, best) }
             s0 = min (s0, (unsigned) __double2loint (sl.y));
             gbest = min (gbest, (unsigned) __double2hiint (sl.y));
-            hsum += sl.x;
+            hsum_acc += sl.x;
+#endif
         }
-        if (NW >= 4)
+        const double hsum = (double) hsum_acc;
+        if (FX_XWARP_F32 && FX_HSUM_F32) { }
+        else if (NW >= 4)
         {
             #pragma unroll
             for (int w = 0; w + 3 < NW; w += 4)
