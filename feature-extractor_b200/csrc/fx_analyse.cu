@@ -64,6 +64,23 @@
 #ifndef FX_PACKED_PASSES
 #define FX_PACKED_PASSES 2                // 0 never, 1 always, 2 for N <= 2048
 #endif
+// FX_ROLE_HIGH 1: the record stage's parts run on the CTA's last warps (the upper bins: fewer peaks on most material) instead of the first
+#ifndef FX_ROLE_HIGH
+#define FX_ROLE_HIGH 1
+#endif
+// FX_PEAK_QUEUE 1: the inharmonicity terms of a warp's peaks are dealt out one per lane from a per-warp queue (see there)
+#ifndef FX_ROLE_PERM
+#define FX_ROLE_PERM 0
+#endif
+#ifndef FX_PEAK_QUEUE
+#define FX_PEAK_QUEUE 0
+#endif
+#ifndef FX_PEAK_QCAP
+#define FX_PEAK_QCAP 64                   // entries per warp and batch (<= 64: 8 holes of 16 bytes; smaller values only to test the batch loop)
+#endif
+#ifndef FX_PACK16
+#define FX_PACK16 0
+#endif
 #ifndef FX_PACK_SPLIT
 #define FX_PACK_SPLIT 0
 #endif
@@ -413,7 +430,17 @@ k_analyse (const AnalyseParams p)
     constexpr int LOG_N = R1 == 16 ? 12 : (R1 == 8 ? 11 : 10);
     // measured per size (profiles/r02_v28_ab_*.txt): the packed filter pass and the |Re| flux test pay 1.2 - 2.1 % at N = 2048 / 1024
     // (no spills there) and cost 2.7 % at N = 4096 (80-register budget: 40 bytes of spills)
+    // FX_ROLE_PERM (experiments): which of the last three warps takes which part -- 0: her, head, flat on NW-1, NW-2, NW-3
+    constexpr int kRp = FX_ROLE_PERM;
+    constexpr int kHi0 = NW - 1, kHi1 = NW >= 2 ? NW - 2 : 0, kHi2 = NW >= 3 ? NW - 3 : 0;
+    constexpr int kRoleHer  = ! FX_ROLE_HIGH ? 0      : (kRp == 0 ? kHi0 : (kRp == 1 ? kHi2 : (kRp == 2 ? kHi0 : kHi1)));
+    constexpr int kRoleHead = ! FX_ROLE_HIGH ? 1 % NW : (kRp == 0 ? kHi1 : (kRp == 1 ? kHi1 : (kRp == 2 ? kHi0 : kHi2)));
+    constexpr int kRoleFlat = ! FX_ROLE_HIGH ? 4 % NW : (kRp == 0 ? kHi2 : (kRp == 1 ? kHi0 : (kRp == 2 ? kHi1 : kHi0)));
     constexpr bool kPackFilter = FX_PACKED_PASSES == 1 || (FX_PACKED_PASSES == 2 && R1 <= 8);
+    // the three parts of the packed filter pass (N = 4096 can be given a subset: FX_PACK16 bit 0 sums of squares, bit 1 the
+    // (x gain, x c1 gain) multiply, bit 2 decay + ramp)
+    constexpr bool kPackSq = kPackFilter || (R1 == 16 && (FX_PACK16 & 1)), kPackXg = kPackFilter || (R1 == 16 && (FX_PACK16 & 2));
+    constexpr bool kPackTail = kPackFilter || (R1 == 16 && (FX_PACK16 & 4));
     constexpr bool kFluxF32Cmp = FX_FLUX_F32CMP == 1 || (FX_FLUX_F32CMP == 2 && R1 <= 8);
     constexpr bool kPsumSlot = FX_PSUM_SLOT == 1 || (FX_PSUM_SLOT == 2 && R1 <= 8);
     constexpr bool kLhrRange = FX_LHR_RANGE == 1 || (FX_LHR_RANGE == 3 && R1 >= 8);
@@ -523,7 +550,7 @@ k_analyse (const AnalyseParams p)
             {
                 const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[r0 + 4 * q]);
                 xs[4 * q] = x4.x; xs[4 * q + 1] = x4.y; xs[4 * q + 2] = x4.z; xs[4 * q + 3] = x4.w;
-                if (kPackFilter)
+                if (kPackSq)
                 {
                     sqp = f2fma (make_float2 (x4.x, x4.y), make_float2 (x4.x, x4.y), sqp); sqp = f2fma (make_float2 (x4.z, x4.w), make_float2 (x4.z, x4.w), sqp);
                 }
@@ -532,7 +559,7 @@ k_analyse (const AnalyseParams p)
                     sq0 = fmaf (x4.x, x4.x, sq0); sq1 = fmaf (x4.y, x4.y, sq1); sq0 = fmaf (x4.z, x4.z, sq0); sq1 = fmaf (x4.w, x4.w, sq1);
                 }
             }
-            if (kPackFilter)
+            if (kPackSq)
             {
                 sq0 = sqp.x; sq1 = sqp.y;
             }
@@ -550,7 +577,7 @@ k_analyse (const AnalyseParams p)
                 if (lane == 0) sm.rms[warp] = r1[0];
 #endif
             }
-            if (kPackFilter)
+            if (kPackXg)
             {
                 // (x gain, x c1 gain) of a sample in one packed multiply: the first half is the windowed path's sample, the second the filter's input
                 #pragma unroll
@@ -612,7 +639,7 @@ k_analyse (const AnalyseParams p)
                                            3.132781128e-08f, 6.512412136e-09f };
             // Both windowed sequences go to the exchange buffer in natural (skewed) order as the packed input of FFT-alpha,
             // z[n] = x[n] w[n] + i y[n] w[n]: the transform's strided gather is then one 8-byte load per point.
-            if (kPackFilter)
+            if (kPackTail)
             {
                 // (two samples per instruction: the neighbour's decaying contribution, the ramp, and each sample's two sequences by its ramp value)
                 #pragma unroll
@@ -625,8 +652,8 @@ k_analyse (const AnalyseParams p)
                     // (what is stored is z / 2 -- see the split below)
                     const float2 w2 = f2fma (make_float2 ((float) j, (float) (j + 1)), make_float2 (wseg_d, wseg_d), make_float2 (wseg_0, wseg_0));
                     float2* zp = &sm.ex[(t >> 4) * D::ROW + 17 * (t & 15) + j];                                                   // tpos (16 t + j)
-                    zp[0] = f2mul (make_float2 (xg[j], y2.x), make_float2 (w2.x, w2.x));
-                    zp[1] = f2mul (make_float2 (xg[j + 1], y2.y), make_float2 (w2.y, w2.y));
+                    zp[0] = f2mul (make_float2 (kPackXg ? xg[j] : __fmul_rn (xs[j], gain), y2.x), make_float2 (w2.x, w2.x));
+                    zp[1] = f2mul (make_float2 (kPackXg ? xg[j + 1] : __fmul_rn (xs[j + 1], gain), y2.y), make_float2 (w2.y, w2.y));
                 }
             }
             else
@@ -1019,7 +1046,7 @@ k_analyse (const AnalyseParams p)
         // The flatness product's continuation (record stage, below) starts from the spectrum bins behind the earliest event
         // thread: its warp fetches the first 32 of them now, from the spectrum stored before the transform.
         float ev_pf = 0.0f;
-        if (warp == 4 % NW)
+        if (warp == kRoleFlat)
         {
             const unsigned ev = warp_minu (lane < NW ? sm.ucodes[lane] : 0xffffffffu);
             const int b = 8 * ((int) ev + 1) + lane;
@@ -1350,7 +1377,7 @@ k_analyse (const AnalyseParams p)
         if (lag_i > 0) f0_bin = (lag_i & (lag_i - 1)) ? idiv_n<N> (lag_i, rcp_approx ((float) lag_i)) : (int) p.f0bin_pow2[__ffs (lag_i) - 1];
         const int ex_base = __ldg (p.ex_off + lag_slot);          // this lag's entries of the exact-ratio table (used below, rarely)
         int her_bin = -1;
-        if (warp == 0 && lane < 18) her_bin = (int) __ldg (&htab[lane]);       // consumed after the next barrier
+        if (warp == kRoleHer && lane < 18) her_bin = (int) __ldg (&htab[lane]);       // consumed after the next barrier
 
         // =========================== harmonic features (HarmonicCharacteristics.h:46-106) =============
         const bool hsilent = hsum < 0.005;                                                        // :88
@@ -1386,58 +1413,94 @@ k_analyse (const AnalyseParams p)
             }
             const int npeaks = __popc (peak_mask);
             // calculateInharmonicity (:212-244) over this thread's peaks
+            // one peak's term of the inharmonicity sum
+            auto peak_term = [&] (int bin) -> double
+            {
+                if (bin == f0_bin) return 0.0;                                                    // :220
+                // bin 0 (:224 start = frpb / 2): the start edge's ratio is exactly twice the end edge's, and that one is N / lag >= 1,
+                // so their floors always differ (:232) and the bin contributes nothing
+                if (bin == 0) return 0.0;
+                const double re = (double) sm.pa[sk32 (bin)];                                     // still Re A
+                const double mg = re * re;
+                // :223-239 compares floor (higher / lower) for the two edges of the bin, start = bin frpb and end = (bin + 1) frpb,
+                // against f0 = sample rate / lag.  Up to an ulp of fp64 rounding these ratios are the rationals bin lag / N
+                // (bin above f0's) or N / (bin lag) (below): unless one of them is an exact integer -- where the reference's own
+                // rounding decides -- their floors are the integer quotients and the fraction is a remainder, no fp64 division.
+                const int pl = bin * lag_i, pl2 = pl + lag_i;
+                bool exact_path = false;
+                int fa = 0, fb = 1;
+                double frac = 0.0;
+                if (bin > f0_bin)
+                {
+                    exact_path = ((pl & (N - 1)) == 0) || ((pl2 & (N - 1)) == 0);
+                    fa = pl >> LOG_N; fb = pl2 >> LOG_N;
+                    frac = (double) (pl & (N - 1)) * (1.0 / (double) N);                          // the smaller ratio is the start edge's
+                }
+                else
+                {
+                    // (not a rare case: a frame analysed at a short lag has every peak below f0's bin)
+                    const float plf2 = (float) pl2, r1 = rcp_approx ((float) pl), r2 = rcp_approx (plf2);
+                    fa = idiv_n<N> (pl, r1); fb = idiv_n<N> (pl2, r2);
+                    const int rem2 = N - fb * pl2;
+                    exact_path = (N - fa * pl == 0) || (rem2 == 0);
+                    // the smaller ratio is the end edge's: fraction rem2 / pl2 < 1 from the fp32 reciprocal with one residual
+                    // correction (relative error ~1e-7 on a term whose sum is compared at 1e-4)
+                    const float q0 = (float) rem2 * r2;
+                    frac = (double) fmaf (fmaf (-q0, plf2, (float) rem2), r2, q0);
+                }
+                if (exact_path)
+                {
+                    // an edge ratio may be an exact integer: the reference's fp64 rounding decides, and its value for this
+                    // (lag, bin) comes from the table the host evaluated in the reference's arithmetic
+                    const int sh = LOG_N - (__ffs (lag_i) - 1);                                   // log2 (N / gcd (lag, N))
+                    int idx;
+                    if (bin > f0_bin) idx = (bin & ((1 << sh) - 1)) == 0 ? 2 * (bin >> sh) : 2 * ((bin + 1) >> sh) + 1;
+                    else              idx = (bin & (bin - 1)) == 0 ? 2 * (__ffs (bin) - 1) - 26 : 2 * (__ffs (bin + 1) - 1) + 1 - 26;
+                    return __ldg (p.ex_tab + (ex_base + idx)) * mg;
+                }
+                return fa == fb ? frac * mg : 0.0;
+            };
+            // calculateInharmonicity (:212-244)
             if (lag_i > 0)                                                                        // :98 f0 > 0
             {
+#if FX_PEAK_QUEUE
+                // A thread holds 0 .. 4 peaks and a warp would run as many rounds as its busiest lane.  The warp's peaks are
+                // compacted into a queue (64 entries in the 16-byte holes of the skewed P / Re A array: 8 holes per warp) and
+                // dealt out one per lane and round: most frames need a single round.  What does not fit stays with its thread.
+                unsigned short* const pq = reinterpret_cast<unsigned short*> (sm.pa + 36 * (8 * warp) + 32);       // entry i: pq[72 (i >> 3) + (i & 7)]
+                int incl = npeaks;
+                #pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync (0xffffffffu, incl, off); if (lane >= off) incl += o; }
+                const int total = __shfl_sync (0xffffffffu, incl, 31);
+                const int pos0 = incl - npeaks;
+                #pragma unroll 1
+                for (int base = 0; base < total; base += FX_PEAK_QCAP)                                      // (warp-uniform; a second batch is rare)
+                {
+                    unsigned m = peak_mask;
+                    int pos = pos0 - base;
+                    #pragma unroll 1
+                    while (m)
+                    {
+                        const int j = __ffs ((int) m) - 1;
+                        m &= m - 1u;
+                        if (pos >= 0 && pos < FX_PEAK_QCAP) pq[72 * (pos >> 3) + (pos & 7)] = (unsigned short) (b0 + j);
+                        ++pos;
+                    }
+                    __syncwarp();
+                    const int nq = min (total - base, FX_PEAK_QCAP);
+                    #pragma unroll 1
+                    for (int i = lane; i < nq; i += 32) inharm += peak_term ((int) pq[72 * (i >> 3) + (i & 7)]);
+                    __syncwarp();
+                }
+#else
                 #pragma unroll 1
                 while (peak_mask)
                 {
                     const int j = __ffs ((int) peak_mask) - 1;
                     peak_mask &= peak_mask - 1u;
-                    const int bin = b0 + j;
-                    if (bin == f0_bin) continue;                                                  // :220
-                    // bin 0 (:224 start = frpb / 2): the start edge's ratio is exactly twice the end edge's, and that one is N / lag >= 1,
-                    // so their floors always differ (:232) and the bin contributes nothing
-                    if (bin == 0) continue;
-                    const double re = (double) sm.pa[pb0 + j];                                    // still Re A: this thread's own bins
-                    const double mg = re * re;
-                    // :223-239 compares floor (higher / lower) for the two edges of the bin, start = bin frpb and end = (bin + 1) frpb,
-                    // against f0 = sample rate / lag.  Up to an ulp of fp64 rounding these ratios are the rationals bin lag / N
-                    // (bin above f0's) or N / (bin lag) (below): unless one of them is an exact integer -- where the reference's own
-                    // rounding decides -- their floors are the integer quotients and the fraction is a remainder, no fp64 division.
-                    const int pl = bin * lag_i, pl2 = pl + lag_i;
-                    bool exact_path = false;
-                    int fa = 0, fb = 1;
-                    double frac = 0.0;
-                    if (bin > f0_bin)
-                    {
-                        exact_path = ((pl & (N - 1)) == 0) || ((pl2 & (N - 1)) == 0);
-                        fa = pl >> LOG_N; fb = pl2 >> LOG_N;
-                        frac = (double) (pl & (N - 1)) * (1.0 / (double) N);                      // the smaller ratio is the start edge's
-                    }
-                    else
-                    {
-                        // (not a rare case: a frame analysed at a short lag has every peak below f0's bin)
-                        const float plf2 = (float) pl2, r1 = rcp_approx ((float) pl), r2 = rcp_approx (plf2);
-                        fa = idiv_n<N> (pl, r1); fb = idiv_n<N> (pl2, r2);
-                        const int rem2 = N - fb * pl2;
-                        exact_path = (N - fa * pl == 0) || (rem2 == 0);
-                        // the smaller ratio is the end edge's: fraction rem2 / pl2 < 1 from the fp32 reciprocal with one residual
-                        // correction (relative error ~1e-7 on a term whose sum is compared at 1e-4)
-                        const float q0 = (float) rem2 * r2;
-                        frac = (double) fmaf (fmaf (-q0, plf2, (float) rem2), r2, q0);
-                    }
-                    if (exact_path)
-                    {
-                        // an edge ratio may be an exact integer: the reference's fp64 rounding decides, and its value for this
-                        // (lag, bin) comes from the table the host evaluated in the reference's arithmetic
-                        const int sh = LOG_N - (__ffs (lag_i) - 1);                               // log2 (N / gcd (lag, N))
-                        int idx;
-                        if (bin > f0_bin) idx = (bin & ((1 << sh) - 1)) == 0 ? 2 * (bin >> sh) : 2 * ((bin + 1) >> sh) + 1;
-                        else              idx = (bin & (bin - 1)) == 0 ? 2 * (__ffs (bin) - 1) - 26 : 2 * (__ffs (bin + 1) - 1) + 1 - 26;
-                        inharm += __ldg (p.ex_tab + (ex_base + idx)) * mg;
-                    }
-                    else if (fa == fb) inharm += frac * mg;
+                    inharm += peak_term (b0 + j);
                 }
+#endif
             }
             const float pkm = ulps_to_margin (pgap);
             // (the normalised magnitudes of :71-77 are not materialised: their sum is magnitudeSum / maxMagnitude up to fp64
@@ -1460,7 +1523,7 @@ k_analyse (const AnalyseParams p)
         // P / Re A array, per-warp slots of earlier phases) is not written again before the next frame's pass 1.
         {
             const bool ld = lane < NW;
-            if (warp == 0 % NW)
+            if (warp == kRoleHer)
             {
                 // calculateHarmonicEnergyCharacteristics (:147-198), numLower = 15, numHarmonics = 3 (:94): lane l < 15 is the
                 // sub-octave f0 / 2^(l+1), lanes 15..17 are the harmonics 1..3 (bins from the table, -1 = not used: a sub-octave in
@@ -1480,7 +1543,7 @@ k_analyse (const AnalyseParams p)
                 }
                 if (lane < 18) rec->her_mx[lane] = mx;
             }
-            if (warp == 1 % NW)
+            if (warp == kRoleHead)
             {
                 float pkm = 1.0f, pmm = 1.0f;
                 if (MG)
@@ -1501,7 +1564,7 @@ k_analyse (const AnalyseParams p)
                 const float flat_margin = warp_min_nonneg (ld ? sm.fmins[0][lane] : 1.0f);
                 if (lane == 0) rec->flat_margin = flat_margin;
             }
-            if (warp == 4 % NW)
+            if (warp == kRoleFlat)
             {
                 // flatness product: without a range event K1b multiplies the warps' totals (flat_state -1); else the offer of the
                 // earliest event thread is continued here
