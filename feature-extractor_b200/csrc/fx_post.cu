@@ -181,27 +181,38 @@ __global__ void __launch_bounds__ (128) k_smooth (const SmoothParams p, long n_t
     if (p.diag) p.diag[(track * p.n_frames + f) * FX_NUM_DIAG + FX_DIAG_ONSET_MARGIN] = om;
 
     // ---- AudioFeatures::getValue for every slot, after both analyser bodies of frame g -------------------
+    // Every history is summed oldest value first like ValueHistory::getTotal.  The ten rows of the window are read once, as
+    // three 16-byte loads each (a row is 48 bytes), and added to the twelve running totals in that order: 30 loads instead of
+    // 120 (the kernel is bound by its load instructions: 0.32 -> 0.1x ms per 1.9e6 rows).
     float sm[FX_NUM_FEATURES];
     const long gr = g - start;                                // frames of this track before this one
     const long rec10 = gr + 1 < 10 ? gr + 1 : 10;
+    float tot[FX_NUM_FEATURES];
+    #pragma unroll
+    for (int k = 0; k < FX_NUM_FEATURES; ++k) tot[k] = 0.0f;
+    float rms2 = 0.0f;                                        // RMS with two pushes per frame: the last five frames, twice each
+    #pragma unroll 1
+    for (long q = g - 9; q <= g; ++q)
+    {
+        if (q < start) continue;
+        const float4* r4 = reinterpret_cast<const float4*> (raw_row (p, track, q));
+        const float4 a = r4[0], b = r4[1], c = r4[2];
+        const float rv[FX_NUM_FEATURES] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w };
+        #pragma unroll
+        for (int k = 0; k < FX_NUM_FEATURES; ++k) tot[k] += rv[k];
+        if (q >= g - 4) { rms2 += rv[FX_RMS]; rms2 += rv[FX_RMS]; }
+    }
+    #pragma unroll
     for (int k = 0; k < FX_NUM_FEATURES; ++k)
     {
-        float total = 0.0f;
-        if (k == FX_ONSET)      { total += onset; sm[k] = total / 1.0f; }
-        else if (k == FX_FLUX)  { total += row[FX_FLUX]; sm[k] = total / 1.0f; }         // depth 1 (RealTimeAnalyser.h:73)
+        if (k == FX_ONSET)      sm[k] = (0.0f + onset) / 1.0f;
+        else if (k == FX_FLUX)  sm[k] = (0.0f + row[FX_FLUX]) / 1.0f;                     // depth 1 (RealTimeAnalyser.h:73)
         else if (k == FX_RMS && p.rms_pushes >= 2)
         {
-            for (long q = g - 4; q <= g; ++q)
-                if (q >= start) { const float r = raw_row (p, track, q)[FX_RMS]; total += r; total += r; }
             const long rec = 2 * (gr + 1) < 10 ? 2 * (gr + 1) : 10;
-            sm[k] = total / (float) (int) rec;
+            sm[k] = rms2 / (float) (int) rec;
         }
-        else
-        {
-            for (long q = g - 9; q <= g; ++q)
-                if (q >= start) total += raw_row (p, track, q)[k];
-            sm[k] = total / (float) (int) rec10;                                          // :84-88
-        }
+        else sm[k] = tot[k] / (float) (int) rec10;                                        // :84-88
     }
     if (p.smooth)
     {
