@@ -854,7 +854,7 @@ k_analyse (const AnalyseParams p)
             ME exc; exc.m = __shfl_up_sync (0xffffffffu, inc.m, 1); exc.e = __shfl_up_sync (0xffffffffu, inc.e, 1);
             if (lane == 0) exc = me_one();
             lprod = exc;                                                                         // lane-exclusive prefix within the warp
-            // The warp's partials leave for K1b from here (the frame record's WarpPart of this warp, one 64-byte run); only what this CTA's own
+            // The warp's partials leave for K1b from here (the frame record's WarpPart of this warp, one 32-byte run); only what this CTA's own
             // threads need -- the magnitude sum, the largest |Re|, the norm of P and the product's warp totals -- also goes
             // through shared memory.  After the transposed butterfly lane l < 8 holds the warp total of value warp_sum_slot<8> (l):
             // 0 S0, 1 W1, 2 flux, 3 lhr, 4 S2, 5 S4, 6 flat_sum (7: zero).
@@ -1624,8 +1624,8 @@ k_analyse (const AnalyseParams p)
 
 // ---------------------------------------------------------------------------------------------------------
 // K1b: the scalar tail of both analyser bodies, one thread per frame, one warp per batch of 32 consecutive frames.
-// A batch's records are one contiguous run of 32 * frame_rec_bytes (10.5 .. 28.5 KB): it arrives in shared memory by ONE
-// bulk copy (a thread reading its own 336 .. 912-byte record straight from global memory touches a different sector with
+// A batch's records are one contiguous run of 32 * frame_rec_bytes (8.5 .. 20.5 KB): it arrives in shared memory by ONE
+// bulk copy (a thread reading its own 272 .. 656-byte record straight from global memory touches a different sector with
 // every load).  The tail is a long dependent fp64 chain (pow, five log10, three sqrt), so it needs many resident warps, and
 // the staged records would cap them: a block of 12 warps therefore shares THREE staging buffers in turn.  Warp w waits for
 // its batch in buffer w % 3, reduces the per-warp partials of its 32 frames into registers, hands the buffer to batch

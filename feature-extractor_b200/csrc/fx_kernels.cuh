@@ -10,6 +10,14 @@
 #ifndef FX_P1SUM_F32
 #define FX_P1SUM_F32 1
 #endif
+// the inharmonicity sum and the mantissa of the flatness product's scan are fp32 across the lanes (fx_analyse.cu); with all
+// three on, every per-warp partial K1 hands to K1b is an fp32 value and the record stores it as one
+#ifndef FX_INHARM_F32
+#define FX_INHARM_F32 1
+#endif
+#ifndef FX_MESCAN_F32
+#define FX_MESCAN_F32 1
+#endif
 
 namespace fx {
 
@@ -19,17 +27,22 @@ constexpr int kMaxOnsetHist = 16;
 
 // What K1 leaves for K1b (k_finalize) per frame: a FrameHead followed by one WarpPart per warp of the K1 CTA (window / 512 of
 // them), frame_rec_bytes (window) per frame.  fp64 wherever the reference accumulates in double.
-// The sums that only K1b looks at leave K1 as PER-WARP partials, stored by each warp where it forms them (one 96-byte run per
+// The sums that only K1b looks at leave K1 as PER-WARP partials, stored by each warp where it forms them (one 64-byte run per
 // warp): K1 reduces across warps only what its own threads need (magnitude sum, maxima, the lag search), and no warp collects
 // the others' partials on its way into the next frame's first barrier (-2.4 % kernel time at N = 2048 / 1024, where the five
 // parts of the old record stage shared four / two warps).  K1b adds them in the order of the butterfly K1 used to run
 // (pairwise tree over the warps), so the features are the same bits.
+#if FX_P1SUM_F32 && FX_INHARM_F32 && FX_MESCAN_F32
+typedef float part_t;              // 64-byte WarpPart: the frame record is 272 / 400 / 656 bytes at N = 1024 / 2048 / 4096
+#else
+typedef double part_t;             // 96-byte WarpPart (336 / 528 / 912 bytes)
+#endif
 struct alignas (16) WarpPart
 {
-    double p1[8];       // pass 1, the transposed butterfly's slots: S0 = sum mag, W1 = sum x mag, flux, low-energy sum, S2 = sum x^2 mag,
+    part_t p1[8];       // pass 1, the transposed butterfly's slots: S0 = sum mag, W1 = sum x mag, flux, low-energy sum, S2 = sum x^2 mag,
                         // S4 = sum mag^2, gated sum, (unused)            (x = (bin + 1/2) / M)
-    double inharm;      // sum of f0Proportion * binMagnitude over the warp's peaks
-    double scan_m;      // extended-range product of the warp's gated magnitudes: mantissa in [0.5, 1) ...
+    part_t inharm;      // sum of f0Proportion * binMagnitude over the warp's peaks
+    part_t scan_m;      // extended-range product of the warp's gated magnitudes: mantissa in [0.5, 1] ...
     int    scan_e;      // ... and exponent
     int    count;       // gated bins
     int    npeaks;
@@ -42,7 +55,7 @@ struct alignas (16) FrameHead
     float  have_prev, lag, pitch_margin, peak_margin, flat_margin;
     float  her_mx[18];             // largest |Re A| around the 15 sub-octave and 3 harmonic bins of f0 (HarmonicCharacteristics.h:147-210), < 0: not used
 };
-static_assert (sizeof (WarpPart) == 96 && sizeof (FrameHead) == 144, "K1b reads the warp parts as runs of 12 doubles behind a 144-byte head");
+static_assert ((sizeof (WarpPart) == 96 || sizeof (WarpPart) == 64) && sizeof (FrameHead) == 144, "the records are runs of 16-byte multiples (bulk copies in K1b)");
 __host__ __device__ constexpr size_t frame_rec_bytes (int window) { return sizeof (FrameHead) + (size_t) (window / 512) * sizeof (WarpPart); }
 
 // ---- K1: per-(track, chunk) frame walker ------------------------------------------------------------
