@@ -26,83 +26,44 @@
 #include "fx_kernels.cuh"
 #include <math.h>
 
-// 1: the spectral features take ONE pass over a thread's bins.  Spread, slope and energy variance are moments about values
-//    (centroid, mean energy, largest magnitude) that are only known after a block reduction; expanded, they are combinations
-//    of raw moments that the first pass can accumulate:  with x = (bin + 1/2) / M, S0 = sum mag, W1 = sum x mag,
-//    S2 = sum x^2 mag, S4 = sum mag^2
-//        sum (x - c)^2 mag        = S2 - 2 c W1 + c^2 S0                       (SpectralCharacteristics.h:135-139)
-//        sum bin * mag / maxE     = (M W1 - S0 / 2) / maxE                     (:175)
-//        sum (mag / maxE - mean)^2 = S4 / maxE^2 - M mean^2                    (:182-190)
-//    in fp64 (the cancellation costs a few of its 16 digits on features compared at 1e-4).  K1b forms them.
-// 0: the second pass over the bins (kept for A/B measurements).
-#ifndef FX_SINGLE_PASS
-#define FX_SINGLE_PASS 1
-#endif
-// FX_WARMUP_ALL_LANES 1: the filter's cross-warp warm-up is computed by every lane from broadcast loads (an independent chain
-//   next to the recurrence) instead of by lane 0 in a divergent tail: same values, -0.4 % kernel time (0 restores the branch).
-// FX_TW2_PREFETCH 1 (experiment, off): stage-2 twiddles loaded before the block barrier inside the transform: +2.2 % (spills).
-#ifndef FX_TW2_PREFETCH
-#define FX_TW2_PREFETCH 0
-#endif
-#ifndef FX_WARMUP_ALL_LANES
-#define FX_WARMUP_ALL_LANES 1
-#endif
-
-// v26 instruction trims (each switch restores the previous form for A/B builds; all but FX_FAST_EPS compute the same values):
+// The spectral features take ONE pass over a thread's bins.  Spread, slope and energy variance are moments about values
+// (centroid, mean energy, largest magnitude) that are only known after a block reduction; expanded, they are combinations
+// of raw moments that the first pass can accumulate:  with x = (bin + 1/2) / M, S0 = sum mag, W1 = sum x mag,
+// S2 = sum x^2 mag, S4 = sum mag^2
+//     sum (x - c)^2 mag        = S2 - 2 c W1 + c^2 S0                       (SpectralCharacteristics.h:135-139)
+//     sum bin * mag / maxE     = (M W1 - S0 / 2) / maxE                     (:175)
+//     sum (mag / maxE - mean)^2 = S4 / maxE^2 - M mean^2                    (:182-190)
+// in fp64 (the cancellation costs a few of its 16 digits on features compared at 1e-4).  K1b forms them.
+//
+// Build switches.  Each restores the previous form of one optimisation so that it can be A/B-timed on a B200 (tools/exp_build.sh,
+// tools/gpu_ab2.sh; the numbers are in DESIGN.md section 7 and profiles/r02_v2*_ab_*.txt).  Several are per window size: at
+// N = 4096 the kernel sits at its 80-register budget and what trims instructions elsewhere makes ptxas spill there.
+// Dropped after measurement and no longer in the source: a MUFU-approximate flatness eps, packed arithmetic in the split, fp32
+// cross-warp sums of rms / magnitude / harmonic sums (spills), a per-warp queue dealing the peaks out one per lane (+1 .. 3 %).
+//   FX_B9_EARLY       the frame's last block barrier stands in front of the peak loop instead of behind it (see there)
+//   FX_ROLE_HIGH      the record stage's parts run on the CTA's last warps (the upper bins: fewer peaks) instead of warps 0 / 1 / 4
+//   FX_PACKED_PASSES  the filter pass (sum of squares, gain, decay, ramp) on packed f32x2 instructions: two samples per
+//                     instruction, IEEE per half, the same values
+//   FX_PACK_LAG       likewise the lag products d^2 s (the same values except the order of a thread's 16-term run sum)
 //   FX_GATHER_GROUPS  FFT-beta's ring gather takes one wrapped base per group of loads that cannot wrap inside (hop >= N / 4)
 //   FX_LAZY_CROSS     the position of a thread's first lag under the threshold is only looked for when its minimum is under it
 //   FX_FLUX_F32CMP    "magnitude rose" decided on |Re| (the magnitudes are exact squares), a predicated add instead of selects
 //   FX_PSUM_SLOT      the norm of P rides in the free eighth slot of pass 1's transposed butterfly
-//   FX_FAST_EPS       the flatness gate's eps = 0.01 log10 (9 rms + 1) from MUFU approximations (1e-6 relative: it gates bins
-//                     whose margin is reported anyway; K1b recomputes the RMS feature itself in double)
-//   FX_B9_EARLY       the frame's last block barrier stands in front of the peak loop instead of behind it (see there)
+//   FX_LHR_RANGE      the low-energy sum is the magnitude sum of the threads below the boundary bin; only the one thread that
+//                     straddles it tests bins
+//   FX_PBASE_F32      the lag search's cumulative sum enters a segment as an fp32 sum of the fp32 warp totals (needs FX_PSCAN_F32)
+//   FX_PREFIX_F32     the mantissa of the flatness product's prefix over the preceding warps is fp32 (needs FX_MESCAN_F32)
 #ifndef FX_B9_EARLY
 #define FX_B9_EARLY 1
 #endif
-//   FX_PACKED_PASSES  filter / window / sum of squares, the split and the lag products on packed f32x2 instructions (two samples, two
-//                     parts or two lags per instruction, IEEE per half: the same values except the order of the 16-term run sums)
-#ifndef FX_PACKED_PASSES
-#define FX_PACKED_PASSES 2                // 0 never, 1 always, 2 for N <= 2048
-#endif
-// FX_ROLE_HIGH 1: the record stage's parts run on the CTA's last warps (the upper bins: fewer peaks on most material) instead of the first
 #ifndef FX_ROLE_HIGH
 #define FX_ROLE_HIGH 1
 #endif
-// FX_PEAK_QUEUE 1: the inharmonicity terms of a warp's peaks are dealt out one per lane from a per-warp queue (see there)
-#ifndef FX_ROLE_PERM
-#define FX_ROLE_PERM 0
-#endif
-#ifndef FX_PEAK_QUEUE
-#define FX_PEAK_QUEUE 0
-#endif
-#ifndef FX_PEAK_QCAP
-#define FX_PEAK_QCAP 64                   // entries per warp and batch (<= 64: 8 holes of 16 bytes; smaller values only to test the batch loop)
-#endif
-#ifndef FX_PACK16
-#define FX_PACK16 0
-#endif
-#ifndef FX_PACK_SPLIT
-#define FX_PACK_SPLIT 0
+#ifndef FX_PACKED_PASSES
+#define FX_PACKED_PASSES 2                // 0 never, 1 always, 2 for N <= 2048
 #endif
 #ifndef FX_PACK_LAG
 #define FX_PACK_LAG 1
-#endif
-//   FX_LHR_RANGE      the low-energy sum is the magnitude sum of the threads below the boundary bin; only the one thread that straddles it tests bins
-//   FX_PBASE_F32      the lag search's cumulative sum enters a segment as an fp32 sum of the fp32 warp totals (needs FX_PSCAN_F32)
-#ifndef FX_LHR_RANGE
-#define FX_LHR_RANGE 3                    // 0 never, 1 always, 3 for N >= 2048 (at N = 1024 it costs 0.8 %: spills)
-#endif
-#ifndef FX_PBASE_F32
-#define FX_PBASE_F32 1
-#endif
-//   FX_XWARP_F32      the cross-warp sums of fp32-accurate warp totals (rms, magnitude sum, harmonic sum) are fp32 chains: every thread
-//                     runs them right behind a barrier, and eight dependent DADDs are twice as long as eight FADDs
-//   FX_PREFIX_F32     likewise the mantissa of the flatness product's prefix over the preceding warps
-#ifndef FX_XWARP_F32
-#define FX_XWARP_F32 0
-#endif
-#ifndef FX_PREFIX_F32
-#define FX_PREFIX_F32 1
 #endif
 #ifndef FX_GATHER_GROUPS
 #define FX_GATHER_GROUPS 1
@@ -116,16 +77,23 @@
 #ifndef FX_PSUM_SLOT
 #define FX_PSUM_SLOT 2                    // 0 never, 1 always, 2 for N <= 2048
 #endif
-#ifndef FX_FAST_EPS
-#define FX_FAST_EPS 0
+#ifndef FX_LHR_RANGE
+#define FX_LHR_RANGE 3                    // 0 never, 1 always, 3 for N >= 2048 (at N = 1024 it costs 0.8 %: spills)
+#endif
+#ifndef FX_PBASE_F32
+#define FX_PBASE_F32 1
+#endif
+#ifndef FX_PREFIX_F32
+#define FX_PREFIX_F32 1
 #endif
 // fp32 warp reductions of sums whose per-thread partials are fp32-accurate anyway (the cross-warp sums stay fp64):
 //   FX_RMS_F32    sum of squares of the frame (16 fp32 squares per thread)
 //   FX_HSUM_F32   harmonic magnitude sum (8 squares per thread)
 //   FX_PSCAN_F32  warp scan of the lag search's cumulative sum (the reference runs this sum in fp32 sequentially, :138-145)
-//   FX_INHARM_F32 inharmonicity sum (a few peaks per thread)
-//   FX_P1SUM_F32  pass 1's seven sums (fp64 per thread over its 8 bins, fp32 across the lanes)
-//   FX_MESCAN_F32 mantissa of the flatness product's warp scan (the exponent is an integer; the product only feeds pow (., 1 / count))
+//   FX_INHARM_F32 inharmonicity sum (a few peaks per thread)                                         (default in fx_kernels.cuh)
+//   FX_P1SUM_F32  pass 1's seven sums (fp64 per thread over its 8 bins, fp32 across the lanes)        (default in fx_kernels.cuh)
+//   FX_MESCAN_F32 mantissa of the flatness product's warp scan (the exponent is an integer; the product only feeds
+//                 pow (., 1 / count))                                                                (default in fx_kernels.cuh)
 #ifndef FX_RMS_F32
 #define FX_RMS_F32 1
 #endif
@@ -134,12 +102,6 @@
 #endif
 #ifndef FX_PSCAN_F32
 #define FX_PSCAN_F32 1
-#endif
-#ifndef FX_INHARM_F32
-#define FX_INHARM_F32 1
-#endif
-#ifndef FX_MESCAN_F32
-#define FX_MESCAN_F32 1
 #endif
 
 namespace fx {
@@ -380,18 +342,8 @@ __device__ __noinline__ void fft_core (V16 io, int m0)
     Smem<R1>& sm = *reinterpret_cast<Smem<R1>*> (fx_smem_raw);
     const int t = threadIdx.x;
     fft_stage1_store<R1, false> (io.v, m0, sm.ex, sm.tw1, sm.tw1f);
-#if FX_TW2_PREFETCH || FX_STAGE23_SHFL
+#if FX_STAGE23_SHFL
     static_assert (! FftDims<R1>::TW2_POWERS, "the experiment paths read the full stage-2 table: build them with -DFX_TW2_POWERS=0");
-#endif
-#if FX_TW2_PREFETCH
-    float2 tw[15];
-    #pragma unroll
-    for (int k = 0; k < 15; ++k) tw[k] = sm.tw2[k * 16 + (t & 15)];
-    __syncthreads();
-    fft_stage2_tw<R1, false> (t, sm.ex, tw);
-    __syncwarp();
-    fft_stage3<R1, false> (t, sm.ex);
-    return;
 #endif
     __syncthreads();
 #if FX_STAGE23_SHFL
@@ -430,17 +382,14 @@ k_analyse (const AnalyseParams p)
     constexpr int LOG_N = R1 == 16 ? 12 : (R1 == 8 ? 11 : 10);
     // measured per size (profiles/r02_v28_ab_*.txt): the packed filter pass and the |Re| flux test pay 1.2 - 2.1 % at N = 2048 / 1024
     // (no spills there) and cost 2.7 % at N = 4096 (80-register budget: 40 bytes of spills)
-    // FX_ROLE_PERM (experiments): which of the last three warps takes which part -- 0: her, head, flat on NW-1, NW-2, NW-3
-    constexpr int kRp = FX_ROLE_PERM;
-    constexpr int kHi0 = NW - 1, kHi1 = NW >= 2 ? NW - 2 : 0, kHi2 = NW >= 3 ? NW - 3 : 0;
-    constexpr int kRoleHer  = ! FX_ROLE_HIGH ? 0      : (kRp == 0 ? kHi0 : (kRp == 1 ? kHi2 : (kRp == 2 ? kHi0 : kHi1)));
-    constexpr int kRoleHead = ! FX_ROLE_HIGH ? 1 % NW : (kRp == 0 ? kHi1 : (kRp == 1 ? kHi1 : (kRp == 2 ? kHi0 : kHi2)));
-    constexpr int kRoleFlat = ! FX_ROLE_HIGH ? 4 % NW : (kRp == 0 ? kHi2 : (kRp == 1 ? kHi0 : (kRp == 2 ? kHi1 : kHi0)));
+    // (which of the three takes which part is immaterial: profiles/r02_v29c_ab_role_permutations_4096.txt)
+    constexpr int kRoleHer  = FX_ROLE_HIGH ? NW - 1 : 0;
+    constexpr int kRoleHead = FX_ROLE_HIGH ? (NW >= 2 ? NW - 2 : 0) : 1 % NW;
+    constexpr int kRoleFlat = FX_ROLE_HIGH ? (NW >= 3 ? NW - 3 : 0) : 4 % NW;
     constexpr bool kPackFilter = FX_PACKED_PASSES == 1 || (FX_PACKED_PASSES == 2 && R1 <= 8);
-    // the three parts of the packed filter pass (N = 4096 can be given a subset: FX_PACK16 bit 0 sums of squares, bit 1 the
-    // (x gain, x c1 gain) multiply, bit 2 decay + ramp)
-    constexpr bool kPackSq = kPackFilter || (R1 == 16 && (FX_PACK16 & 1)), kPackXg = kPackFilter || (R1 == 16 && (FX_PACK16 & 2));
-    constexpr bool kPackTail = kPackFilter || (R1 == 16 && (FX_PACK16 & 4));
+    // (its three parts -- sums of squares, the (x gain, x c1 gain) multiply, decay + ramp -- were also timed alone at N = 4096:
+    // 0 / +0.1 / +2.1 %, profiles/r02_v29a_ab_4096.txt)
+    constexpr bool kPackSq = kPackFilter, kPackXg = kPackFilter, kPackTail = kPackFilter;
     constexpr bool kFluxF32Cmp = FX_FLUX_F32CMP == 1 || (FX_FLUX_F32CMP == 2 && R1 <= 8);
     constexpr bool kPsumSlot = FX_PSUM_SLOT == 1 || (FX_PSUM_SLOT == 2 && R1 <= 8);
     constexpr bool kLhrRange = FX_LHR_RANGE == 1 || (FX_LHR_RANGE == 3 && R1 >= 8);
@@ -566,11 +515,7 @@ k_analyse (const AnalyseParams p)
             {
 #if FX_RMS_F32
                 const float wsq = warp_sumf (sq0 + sq1);
-#if FX_XWARP_F32
-                if (lane == 0) reinterpret_cast<float*> (sm.rms)[warp] = wsq;
-#else
                 if (lane == 0) sm.rms[warp] = (double) wsq * ((double) gain * (double) gain);      // AudioDataCollector.h:88 applies the gain
-#endif
 #else
                 double r1[1] = { (double) (sq0 + sq1) * ((double) gain * (double) gain) };       // AudioDataCollector.h:88 applies the gain
                 warp_sum<1> (r1);
@@ -598,7 +543,6 @@ k_analyse (const AnalyseParams p)
                 #pragma unroll
                 for (int j = 1; j < 16; ++j) { y = fmaf (c2, y, __fmul_rn (xs[j], c1g)); ys[j] = y; }
             }
-#if FX_WARMUP_ALL_LANES
             // every lane runs the warm-up of its WARP's first segment from broadcast loads (one wavefront each): an independent
             // chain the scheduler can interleave with the recurrence above, instead of a divergent tail behind it
             float ywarm = 0.0f;
@@ -614,25 +558,6 @@ k_analyse (const AnalyseParams p)
             }
             float yin = __shfl_up_sync (0xffffffffu, y, 1);
             if (lane == 0) yin = (t != 0) ? ywarm : 0.0f;
-#else
-            float yin = __shfl_up_sync (0xffffffffu, y, 1);
-            if (lane == 0)
-            {
-                yin = 0.0f;
-                if (t != 0)
-                {
-                    // the left neighbour lives in another warp: warm up over its last 12 samples (e^(-pi/2)^12 = 6.5e-9)
-                    const int rp = sk32 ((int) ((a0 + n0 - 12) & (N - 1)));
-                    #pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                    {
-                        const float4 x4 = *reinterpret_cast<const float4*> (&sm.ring[rp + 4 * q]);
-                        yin = fmaf (c2, yin, __fmul_rn (x4.x, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.y, c1g));
-                        yin = fmaf (c2, yin, __fmul_rn (x4.z, c1g)); yin = fmaf (c2, yin, __fmul_rn (x4.w, c1g));
-                    }
-                }
-            }
-#endif
             // e^(-pi/2 (j+1)): the filter constant is fixed by AudioFilter::m = 2 (RealTimeAudioAnalysis.h:127)
             constexpr float kDecay[12] = { 2.078795764e-01f, 4.321391826e-02f, 8.983291021e-03f, 1.867442732e-03f, 3.882032039e-04f,
                                            8.069951757e-05f, 1.677578152e-05f, 3.487342356e-06f, 7.249472516e-07f, 1.507017275e-07f,
@@ -707,12 +632,7 @@ k_analyse (const AnalyseParams p)
             {
                 const float2 zk = sm.ex[zb_own + zrun<R1> (j)];                                // Z[k], k = b0 + j
                 const float2 zn = sm.ex[j == 0 ? zb_self : zb_mirror + zrun<R1> (8 - j)];      // Z[(N - k) & (N - 1)]
-#if FX_PACK_SPLIT
-                const float2 sum = f2add (zk, zn);
-                const float reB = sum.x, reC = sum.y;
-#else
                 const float reB = zk.x + zn.x, reC = zk.y + zn.y;
-#endif
                 const float imB = zk.y - zn.y;
                 cr[j] = reB;
                 if (b0 < M / 2) rawmax = fmaxf (rawmax, fmaxf (fabsf (reB), fabsf (imB)));
@@ -725,16 +645,6 @@ k_analyse (const AnalyseParams p)
         }
 
         // RMS (RealTimeAnalyser.h:207-208)
-#if FX_XWARP_F32 && FX_RMS_F32
-        float rms_sumf = 0.0f;
-        #pragma unroll
-        for (int w = 0; w < NW; w += 2)
-        {
-            const float2 r2 = *reinterpret_cast<const float2*> (&reinterpret_cast<const float*> (sm.rms)[w]);
-            rms_sumf += r2.x; rms_sumf += r2.y;
-        }
-        const double rms_sum = (double) rms_sumf * ((double) gain * (double) gain);                // AudioDataCollector.h:88 applies the gain
-#else
         double rms_sum = 0.0;
         #pragma unroll
         for (int w = 0; w < NW; w += 2)
@@ -742,16 +652,9 @@ k_analyse (const AnalyseParams p)
             const double2 r2 = *reinterpret_cast<const double2*> (&sm.rms[w]);
             rms_sum += r2.x; rms_sum += r2.y;
         }
-#endif
         // K1b recomputes both in double for the RMS feature; here they only set the flatness gate, whose margin is reported
-#if FX_FAST_EPS
-        float rms, log_rms;
-        asm ("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rms) : "f"((float) (rms_sum * (1.0 / (double) N))));
-        log_rms = __log2f (fmaf (rms, 9.0f, 1.0f)) * 0.30102999566f;
-#else
         const float rms = __fsqrt_rn ((float) (rms_sum * (1.0 / (double) N)));
         const float log_rms = log10f (__fadd_rn (__fmul_rn (rms, 9.0f), 1.0f));
-#endif
         const double eps = 0.01 * (double) log_rms;                                               // SpectralCharacteristics.h:108
 
         // =========================== spectral features, pass 1 ========================================
@@ -869,20 +772,12 @@ k_analyse (const AnalyseParams p)
             {
                 wp->count = wcount; wp->rawmax = wraw;
                 // S0: every thread needs the magnitude sum
-#if FX_XWARP_F32 && FX_P1SUM_F32
-                *reinterpret_cast<float4*> (&sm.p1s[warp]) = make_float4 ((float) s8[0], 0.0f, wmax, wps);
-#else
                 *reinterpret_cast<double2*> (&sm.p1s[warp]) = make_double2 ((double) s8[0], __hiloint2double (__float_as_int (wps), __float_as_int (wmax)));
-#endif
                 if (MG) sm.fmins[0][warp] = wmar;
             }
         }
         __syncthreads();
-#if FX_XWARP_F32 && FX_P1SUM_F32
-        float mag_sum_acc = 0.0f;
-#else
         double mag_sum_acc = 0.0;
-#endif
         float maxre_all = 0.0f, psum_all = 0.0f;
         ME prefix = me_one();
         float pfm = 0.5f; int pfe = 1; (void) pfm; (void) pfe;
@@ -891,17 +786,10 @@ k_analyse (const AnalyseParams p)
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-#if FX_XWARP_F32 && FX_P1SUM_F32
-            const float4 sl = *reinterpret_cast<const float4*> (&sm.p1s[w]);                      // one LDS.128: { s0, -, maxre, psum }
-            mag_sum_acc += sl.x;
-            maxre_all = fmaxf (maxre_all, sl.z);
-            psum_all += sl.w;
-#else
             const double2 sl = *reinterpret_cast<const double2*> (&sm.p1s[w]);                    // one LDS.128: { s0, (maxre, psum) }
             mag_sum_acc += sl.x;
             maxre_all = fmaxf (maxre_all, __int_as_float (__double2loint (sl.y)));
             psum_all += __int_as_float (__double2hiint (sl.y));
-#endif
         }
         const double mag_sum = (double) mag_sum_acc;
         #pragma unroll 1
@@ -1226,11 +1114,7 @@ k_analyse (const AnalyseParams p)
             const float wm = warp_max_nonneg (hmaxre);
             if (lane == 0)
             {
-#if FX_XWARP_F32 && FX_HSUM_F32
-                *reinterpret_cast<float4*> (&sm.lags[warp]) = make_float4 ((float) s1[0], wm, __uint_as_float (wfc), __uint_as_float (wbest));
-#else
                 *reinterpret_cast<double2*> (&sm.lags[warp]) = make_double2 (s1[0], __hiloint2double ((int) wbest, (int) wfc));
-#endif
                 sm.hmaxs[warp] = wm;
             }
         }
@@ -1238,31 +1122,18 @@ k_analyse (const AnalyseParams p)
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
         unsigned s0 = 0xffffffffu;
         unsigned gbest = 0xffffffffu;                              // bit pattern of the smallest cnd of the search range
-#if FX_XWARP_F32 && FX_HSUM_F32
-        float hsum_acc = 0.0f;
-#else
         double hsum_acc = 0.0;
-#endif
         float hmaxre = 0.0f;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
-#if FX_XWARP_F32 && FX_HSUM_F32
-            const float4 sl = *reinterpret_cast<const float4*> (&sm.lags[w]);                     // one LDS.128: { hsum, largest |Re A|, first_cross, best }
-            s0 = min (s0, __float_as_uint (sl.z));
-            gbest = min (gbest, __float_as_uint (sl.w));
-            hsum_acc += sl.x;
-            hmaxre = fmaxf (hmaxre, sl.y);
-#else
             const double2 sl = *reinterpret_cast<const double2*> (&sm.lags[w]);                   // one LDS.128: { hsum, (first_cross, best) }
             s0 = min (s0, (unsigned) __double2loint (sl.y));
             gbest = min (gbest, (unsigned) __double2hiint (sl.y));
             hsum_acc += sl.x;
-#endif
         }
         const double hsum = (double) hsum_acc;
-        if (FX_XWARP_F32 && FX_HSUM_F32) { }
-        else if (NW >= 4)
+        if (NW >= 4)
         {
             #pragma unroll
             for (int w = 0; w + 3 < NW; w += 4)
@@ -1463,36 +1334,6 @@ k_analyse (const AnalyseParams p)
             // calculateInharmonicity (:212-244)
             if (lag_i > 0)                                                                        // :98 f0 > 0
             {
-#if FX_PEAK_QUEUE
-                // A thread holds 0 .. 4 peaks and a warp would run as many rounds as its busiest lane.  The warp's peaks are
-                // compacted into a queue (64 entries in the 16-byte holes of the skewed P / Re A array: 8 holes per warp) and
-                // dealt out one per lane and round: most frames need a single round.  What does not fit stays with its thread.
-                unsigned short* const pq = reinterpret_cast<unsigned short*> (sm.pa + 36 * (8 * warp) + 32);       // entry i: pq[72 (i >> 3) + (i & 7)]
-                int incl = npeaks;
-                #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync (0xffffffffu, incl, off); if (lane >= off) incl += o; }
-                const int total = __shfl_sync (0xffffffffu, incl, 31);
-                const int pos0 = incl - npeaks;
-                #pragma unroll 1
-                for (int base = 0; base < total; base += FX_PEAK_QCAP)                                      // (warp-uniform; a second batch is rare)
-                {
-                    unsigned m = peak_mask;
-                    int pos = pos0 - base;
-                    #pragma unroll 1
-                    while (m)
-                    {
-                        const int j = __ffs ((int) m) - 1;
-                        m &= m - 1u;
-                        if (pos >= 0 && pos < FX_PEAK_QCAP) pq[72 * (pos >> 3) + (pos & 7)] = (unsigned short) (b0 + j);
-                        ++pos;
-                    }
-                    __syncwarp();
-                    const int nq = min (total - base, FX_PEAK_QCAP);
-                    #pragma unroll 1
-                    for (int i = lane; i < nq; i += 32) inharm += peak_term ((int) pq[72 * (i >> 3) + (i & 7)]);
-                    __syncwarp();
-                }
-#else
                 #pragma unroll 1
                 while (peak_mask)
                 {
@@ -1500,7 +1341,6 @@ k_analyse (const AnalyseParams p)
                     peak_mask &= peak_mask - 1u;
                     inharm += peak_term (b0 + j);
                 }
-#endif
             }
             const float pkm = ulps_to_margin (pgap);
             // (the normalised magnitudes of :71-77 are not materialised: their sum is magnitudeSum / maxMagnitude up to fp64
@@ -1727,7 +1567,7 @@ __global__ void __launch_bounds__ (kFinalizeRows, FX_FZ_BLOCKS) k_finalize (cons
     const double eps = 0.01 * (double) log_rms;                                                   // :108
     const bool silent = ! (r.mag_sum > 0.05);                                                     // :121-123
     // K1 leaves raw moments over x = (bin + 1/2) / M = fc / nyquist: W1 = sum x mag, S2 = sum x^2 mag, S4 = sum mag^2
-    // (see FX_SINGLE_PASS at the top of this file)
+    // (see the top of this file)
     const float  centroid = (float) ((w1 * nyquist) / r.mag_sum);                                 // :127 weighted / magSum
     const double cn = (double) centroid / nyquist;                                                // :137
     const double var = (s2 - 2.0 * cn * w1) + cn * cn * r.mag_sum;                                // :135-139
