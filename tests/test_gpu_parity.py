@@ -49,7 +49,7 @@ CASES = [
     (4096, 2048, 96000.0, 8, 2.0),
     (2048, 64, 48000.0, 2, 0.5),             # many hops per window
     (1024, 1024, 44100.0, 4, 2.0),           # no overlap at all
-    (1024, 16, 44100.0, 2, 0.06),            # the smallest hop: windows start off the ring's 32-sample groups, 4 copying threads per hop
+    (1024, 16, 44100.0, 2, 1.0),             # the smallest hop: windows start off the ring's 32-sample groups, 4 copying threads per hop
     (4096, 32, 48000.0, 1, 0.1),             # 128 hops per window
 ]
 
