@@ -8,10 +8,11 @@
 // features on the un-windowed frame, integer pitch lag, raw fp64 flatness product with IEEE under/overflow,
 // previous spectrum not updated on silent frames.
 //
-// Data movement: the hop's new samples arrive by cp.async.bulk (TMA bulk copy, mbarrier completion) into a
-// shared-memory ring holding the N-sample window, so each input sample crosses HBM once per chunk; the next
-// hop is prefetched as soon as the frame's last read of the ring is behind a barrier and lands during the pitch /
-// harmonic passes.
+// Data movement: the hop's new samples arrive as 16-byte asynchronous copies (cp.async / LDGSTS, completion handed to an
+// mbarrier) in a SKEWED shared-memory ring holding the N-sample window, so each input sample crosses HBM once per chunk and
+// the float4 reads of the filter pass are bank-conflict free; the next hop is prefetched as soon as the frame's last read of
+// the ring is behind a barrier and lands during the pitch / harmonic passes.  K1b streams K1's records through shared
+// memory with cp.async.bulk (the TMA bulk copy).
 // The reference runs four real-input transforms per hop; here they are packed into TWO complex FFTs, both through
 // ONE out-of-line copy of the FFT code (the kernel is instruction-cache bound otherwise):
 //   FFT-alpha  z = x w + i onepole (x) w   -> B = FFT (x w): Re B (+ Im B for the slope quirk), C: P[k] = Re C[k]^2,
