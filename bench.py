@@ -532,6 +532,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 FFT / f64 reductions", "data": "synthetic", "config": config_dict(args, world),
+            "dtype_note": "every sum is fp64 per thread (as the reference accumulates) and across the warps; across the 32 lanes of a warp the partials, "
+                          "fp32-accurate squares of an fp32 spectrum, are added in fp32 (max abs error of the parity report 3.7e-5 at a 1e-4 tolerance)",
             "e2e": e2e, "e2e_pcm16": e2e_pcm, "h2d_probe": h2d_probe, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": f"k_analyse<{WINDOW // 256}>", "achieved": flops / k1_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": flops / k1_s / 1e12 / fp32_peak if fp32_peak else None, "traffic": traffic,
