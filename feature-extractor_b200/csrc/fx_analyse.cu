@@ -22,7 +22,8 @@
 //              (PitchAnalyser.h:120), which is all that can reach the lag search (PitchAnalyser.h:163)
 // K1 leaves the per-frame sums in a FrameRec; K1b (one thread per frame) applies the scalar tail of the
 // reference (pow / log10 / sqrt, clamps, gates) so that no serial libm code sits inside the frame loop.
-// All feature reductions accumulate in fp64 like the reference.  No tensor cores: nothing here is a GEMM.
+// Every sum accumulates in fp64 per thread like the reference, and across the warps; across the 32 lanes of a warp the
+// partials (fp32-accurate squares of an fp32 spectrum) are added in fp32.  No tensor cores: nothing here is a GEMM.
 #include "fx_fft.cuh"
 #include "fx_kernels.cuh"
 #include <math.h>
