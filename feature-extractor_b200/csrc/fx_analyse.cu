@@ -88,6 +88,11 @@
 #ifndef FX_PREFIX_F32
 #define FX_PREFIX_F32 1
 #endif
+//   FX_LAGSLOT_F32    the lag search's per-warp slot carries the harmonic sum as the fp32 value it is, next to the largest |Re A|: the
+//                     cross-warp sum behind the barrier is an FADD chain and the separate maxima loads go (needs FX_HSUM_F32)
+#ifndef FX_LAGSLOT_F32
+#define FX_LAGSLOT_F32 1
+#endif
 // fp32 warp reductions of sums whose per-thread partials are fp32-accurate anyway (the cross-warp sums stay fp64):
 //   FX_RMS_F32    sum of squares of the frame (16 fp32 squares per thread)
 //   FX_HSUM_F32   harmonic magnitude sum (8 squares per thread)
@@ -1116,16 +1121,32 @@ k_analyse (const AnalyseParams p)
             const float wm = warp_max_nonneg (hmaxre);
             if (lane == 0)
             {
+#if FX_LAGSLOT_F32 && FX_HSUM_F32
+                *reinterpret_cast<float4*> (&sm.lags[warp]) = make_float4 ((float) s1[0], wm, __uint_as_float (wfc), __uint_as_float (wbest));
+#else
                 *reinterpret_cast<double2*> (&sm.lags[warp]) = make_double2 (s1[0], __hiloint2double ((int) wbest, (int) wfc));
                 sm.hmaxs[warp] = wm;
+#endif
             }
         }
         __syncthreads();
         // ---- every thread now derives the lag on its own (all control flow below is uniform across the CTA) -----------
         unsigned s0 = 0xffffffffu;
         unsigned gbest = 0xffffffffu;                              // bit pattern of the smallest cnd of the search range
-        double hsum_acc = 0.0;
         float hmaxre = 0.0f;
+#if FX_LAGSLOT_F32 && FX_HSUM_F32
+        float hsum_acc = 0.0f;
+        #pragma unroll
+        for (int w = 0; w < NW; ++w)
+        {
+            const float4 sl = *reinterpret_cast<const float4*> (&sm.lags[w]);                     // one LDS.128: { hsum, largest |Re A|, first_cross, best }
+            s0 = min (s0, __float_as_uint (sl.z));
+            gbest = min (gbest, __float_as_uint (sl.w));
+            hsum_acc += sl.x;
+            hmaxre = fmaxf (hmaxre, sl.y);
+        }
+#else
+        double hsum_acc = 0.0;
         #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
@@ -1134,8 +1155,10 @@ k_analyse (const AnalyseParams p)
             gbest = min (gbest, (unsigned) __double2hiint (sl.y));
             hsum_acc += sl.x;
         }
+#endif
         const double hsum = (double) hsum_acc;
-        if (NW >= 4)
+        if (FX_LAGSLOT_F32 && FX_HSUM_F32) { }
+        else if (NW >= 4)
         {
             #pragma unroll
             for (int w = 0; w + 3 < NW; w += 4)
